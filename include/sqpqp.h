@@ -1,0 +1,189 @@
+/*
+ * sqpqp.h -- C ABI of the B200-native QP-subproblem engine for SqpSolver.jl.
+ *
+ * This is the drop-in boundary: the entry points below are what SqpSolver.jl's
+ * Julia host would bind with `ccall` (see INTEGRATION.md and
+ * sqpsolver.jl_b200/julia/SqpQpB200.jl) in place of the JuMP->MOI->Ipopt path the
+ * reference takes in src/algorithms/subproblem_JuMP.jl.  Each function cites the
+ * reference code it replaces.
+ *
+ * Conventions
+ *   - return 0 = OK, < 0 = error (see SQPQP_E_*); solver outcome is DATA
+ *     (`moi_status`), never an error code.
+ *   - no C++ exceptions, no callbacks cross the boundary.
+ *   - all pointers are HOST pointers owned by the caller unless the function name
+ *     ends in `_device`; they are only read/written during the call.
+ *   - all device memory, pinned staging buffers and the CUDA stream are owned by
+ *     the handle.  A handle is not thread-safe; different handles are independent.
+ *   - per-instance arrays of a batch are instance-major: a[b*len + i].
+ *     A single NLP is a batch of 1.
+ *   - indices in COO inputs are 1-based int64 exactly as MOI hands them to
+ *     SqpSolver (src/MOI_wrapper.jl:930-945, 1010-1025).
+ *   - multipliers come back in the reference's storage convention
+ *     (subproblem_JuMP.jl:514-563): lambda in MOI sign (grad = J' lambda + r),
+ *     mult_x_L = max(r,0) >= 0, mult_x_U = min(r,0) <= 0.
+ */
+#ifndef SQPQP_H
+#define SQPQP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sqpqp_handle_s* sqpqp_handle;
+
+/* error codes */
+#define SQPQP_OK 0
+#define SQPQP_E_BADARG (-1)
+#define SQPQP_E_CUDA (-2)
+#define SQPQP_E_NOMEM (-3)
+#define SQPQP_E_STATE (-4) /* call order violated (e.g. solve before setup/update) */
+
+/* moi_status values == Integer(MOI.TerminationStatusCode) in MathOptInterface v1 */
+#define SQPQP_MOI_OPTIMIZE_NOT_CALLED 0
+#define SQPQP_MOI_OPTIMAL 1
+#define SQPQP_MOI_INFEASIBLE 2
+#define SQPQP_MOI_LOCALLY_SOLVED 4
+#define SQPQP_MOI_LOCALLY_INFEASIBLE 5
+#define SQPQP_MOI_ALMOST_LOCALLY_SOLVED 10
+#define SQPQP_MOI_ITERATION_LIMIT 11
+#define SQPQP_MOI_NUMERICAL_ERROR 20
+
+/* phases of sqpqp_solve_tr */
+#define SQPQP_PHASE_QP 0  /* sub_optimize!      subproblem_JuMP.jl:127-183 */
+#define SQPQP_PHASE_FR 1  /* sub_optimize_FR!   subproblem_JuMP.jl:352-393 */
+#define SQPQP_PHASE_SOC 2 /* sub_optimize_soc!  sqp_trust_region.jl:341-360 (E_override = g(x+p) - J p) */
+#define SQPQP_PHASE_LP 3  /* sub_optimize_lp    subproblem_JuMP.jl:185-244 (start-point projection) */
+
+/* Per-instance solve statistics (all counters are exact, measured on device). */
+typedef struct sqpqp_info {
+    int32_t moi_status;
+    int32_t admm_iters;
+    int32_t cg_iters;        /* PCG iterations inside ADMM x-updates */
+    int32_t polish_tries;
+    int32_t polish_cg_iters; /* PCG iterations inside polish solves */
+    int32_t polished;        /* 1: returned point is the verified active-set (KKT) refinement */
+    int32_t rho_updates;
+    int32_t checks;          /* residual checks (3 SpMV each) */
+    double rho;              /* final ADMM step size (scaled space) */
+    double rho_box_floor;    /* 1.5*|lambda_min(P_scaled)| -- nonconvexity guard, 0 if P >= 0 */
+    double res_prim;         /* unscaled inf-norm primal residual of the returned point */
+    double res_dual;         /* unscaled inf-norm dual residual of the returned point */
+    double objective;        /* 1/2 p'Pp + q'p at the returned point */
+} sqpqp_info;
+
+/* Solver options (defaults via sqpqp_default_options). */
+typedef struct sqpqp_options {
+    double rho0, sigma, alpha;
+    double eps_abs, eps_rel, eps_inf;
+    double rho_eq_mult, rho_min, rho_max, adapt_tol;
+    double cg_rel0;          /* PCG stops at cg_rel0 * |residual of the warm start| */
+    double rb_full_mult;     /* rho_box floor = rb_full_mult * max(0,-lambda_min(P_scaled)) */
+    double polish_trigger, polish_rho, polish_tol, feas_tol, dual_tol;
+    int32_t max_iter, check_every, ruiz_iters, cg_max, eig_iters, polish_outer, polish_cg_max;
+    int32_t warm_start;      /* 1: start ADMM from the previous solve's (p, y) of the same instance */
+    int32_t team;            /* 0 auto, 1 one CTA per instance, 2 whole grid per instance (cooperative) */
+    int32_t threads;         /* CTA size (multiple of 32); 0 = auto */
+} sqpqp_options;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+/* One handle = one CUDA device + one stream + owned device/pinned buffers. */
+int sqpqp_create(sqpqp_handle* h, int device_ordinal);
+int sqpqp_destroy(sqpqp_handle h);
+const char* sqpqp_last_error(sqpqp_handle h);
+void sqpqp_default_options(sqpqp_options* o);
+int sqpqp_set_options(sqpqp_handle h, const sqpqp_options* o);
+/* CUDA stream of the handle as a void* (cudaStream_t), for callers that time or
+ * enqueue work on the same stream. */
+void* sqpqp_stream(sqpqp_handle h);
+
+/* ---- NLP lane (fast lane B2: QpDevice <: AbstractSubOptimizer) --------------------- */
+/* Replaces the SqpTR constructor's pattern build (sqp_trust_region.jl:41-57:
+ * sparse(j_row,j_col,ones,m,n), sparse(h_row,h_col,ones,n,n)) and create_model!
+ * (subproblem_JuMP.jl:36-125: slack columns for rows > m_lin, 2 per two-sided row).
+ * Builds on device, once: CSR(J | slack cols), CSR of its transpose (== Julia's CSC
+ * of J), the symmetric-full CSR(H) of sqp.jl:92-103, and the ordered-duplicate
+ * scatter permutations.  `batch` instances share the pattern and x_L/x_U/g_L/g_U
+ * finiteness; bounds are given per instance when bounds_per_instance != 0
+ * (instance-major), else once.  +-Inf allowed in bounds. */
+int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t m, int32_t m_lin,
+                    int64_t nnz_j, const int64_t* j_row, const int64_t* j_col,
+                    int64_t nnz_h, const int64_t* h_row, const int64_t* h_col,
+                    const double* x_L, const double* x_U, const double* g_L, const double* g_U,
+                    int32_t bounds_per_instance);
+
+/* Replaces eval_functions!/eval_Jacobian! scatter (sqp.jl:86-117) and the QpData
+ * refresh (sqp.jl:66-79): dE[batch][nnz_j], h_val[batch][nnz_h] (may be NULL: no
+ * Hessian), df[batch][n], E[batch][m], lambda is NOT needed (already folded in h_val).
+ * Host arrays are copied to pinned staging and uploaded asynchronously; duplicates
+ * are summed in ascending COO order starting from 0.0 (bit-exact with the reference). */
+int sqpqp_update_nlp(sqpqp_handle h, const double* dE, const double* h_val, const double* df, const double* E);
+/* Same, with DEVICE pointers (no staging, no copy): for a device-side evaluator. */
+int sqpqp_update_nlp_device(sqpqp_handle h, const double* dE, const double* h_val, const double* df, const double* E);
+
+/* Replaces sub_optimize! / sub_optimize_FR! / sub_optimize_soc! / sub_optimize_lp +
+ * set_trust_region! + modify_constraints! + collect_solution!
+ * (subproblem_JuMP.jl:127-183, 352-393, 185-244, 432-448, 465-512, 514-563).
+ *   x_k[batch][n], delta[batch]; E_override[batch][m] only for SQPQP_PHASE_SOC else NULL;
+ *   active[batch] (may be NULL = all): instances with active[b]==0 are skipped and
+ *   their outputs left untouched.
+ * Outputs (any may be NULL): p[batch][n] (for PHASE_LP: the projected x),
+ *   lambda[batch][m], mult_x_L/U[batch][n], slack[batch][S], moi_status[batch],
+ *   info[batch].  Blocking. */
+int sqpqp_solve_tr(sqpqp_handle h, int32_t phase, const double* x_k, const double* delta,
+                   const double* E_override, const int32_t* active,
+                   double* p, double* lambda, double* mult_x_L, double* mult_x_U, double* slack,
+                   int32_t* moi_status, sqpqp_info* info);
+/* Number of slack columns S (order: for each row i > m_lin: u_i, then v_i if two-sided). */
+int sqpqp_num_slacks(sqpqp_handle h, int32_t* S);
+
+/* Merit / model arithmetic of the ratio test on device:
+ *   norm_violations (common.jl:54-77, p=1), compute_phi (sqp.jl:170-183),
+ *   compute_qmodel (sqp_trust_region.jl:487-508).
+ * Inputs per instance: x[n], p[n], E_trial[m] = g(x+p) and f_trial = f(x+p) from the
+ * host callbacks, mu, fr (feasibility-restoration flag).  Uses the E, df, J, H of the
+ * last update_nlp.  Outputs per instance (any may be NULL):
+ *   viol0 = |viol(E,x)|_1, viol_trial = |viol(E_trial,x+p)|_1,
+ *   phi_trial = f_trial + mu*viol_trial (or viol_trial if fr),
+ *   q0 = mu*viol0, qk = df'p + 1/2 p'Hp + mu*|viol(E+Jp, x+p)|_1. */
+int sqpqp_merit(sqpqp_handle h, const double* x, const double* p, const double* E_trial, const double* f_trial,
+                const double* mu, const int32_t* fr,
+                double* viol0, double* viol_trial, double* phi_trial, double* q0, double* qk);
+/* KT_residuals (common.jl:14-23) as coded, per instance. */
+int sqpqp_kt_residuals(sqpqp_handle h, const double* lambda, const double* mult_x_U, const double* mult_x_L,
+                       double* kt);
+
+/* out[batch][m] = J p per instance (`Jacobian * p`, sqp_trust_region.jl:343, 492). */
+int sqpqp_jac_times(sqpqp_handle h, const double* p, double* out);
+
+/* Read back the device matrices of instance b (parity tests): CSR of J (m x n, slack
+ * columns excluded), CSR of J' (n x m) and symmetric CSR of H.  Pass NULL to skip.
+ * which: 0 = J, 1 = J transposed, 2 = H.  nnz query: pass row_ptr=NULL. */
+int sqpqp_get_csr(sqpqp_handle h, int32_t which, int32_t b, int64_t* nnz, int32_t* row_ptr, int32_t* col_idx,
+                  double* values);
+
+/* ---- generic QP lane (boundary B1: what an MOI.AbstractOptimizer shim sees) -------- */
+/*   min 1/2 x'Px + q'x   s.t.  rl <= A x <= ru,  cl <= x <= cu
+ * P is given as MOI ScalarQuadraticTerm triplets (one triangle; an off-diagonal
+ * term c means P_ij = P_ji = c, a diagonal term c means P_ii = c; duplicates add),
+ * A as 1-based triplets.  Equivalent to the NLP lane with m_lin = 0, E = 0, x_k = 0,
+ * delta = +Inf. */
+int sqpqp_qp_setup(sqpqp_handle h, int32_t nv, int32_t nc, int64_t nnz_p, const int64_t* p_row, const int64_t* p_col,
+                   int64_t nnz_a, const int64_t* a_row, const int64_t* a_col);
+int sqpqp_qp_solve(sqpqp_handle h, const double* p_val, const double* q, const double* a_val,
+                   const double* rl, const double* ru, const double* cl, const double* cu,
+                   double* x, double* row_dual, double* col_dual, int32_t* moi_status, sqpqp_info* info);
+
+/* ---- introspection ----------------------------------------------------------------- */
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+int64_t sqpqp_launch_count(sqpqp_handle h);
+/* Device time (ms) of the last sqpqp_solve_tr's solve kernel, from CUDA events on
+ * the handle's stream. */
+double sqpqp_last_solve_ms(sqpqp_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQPQP_H */

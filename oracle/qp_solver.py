@@ -132,6 +132,12 @@ def solve_qp(P, q, A, rl, ru, xl, xu, x0=None, tol=1e-10, max_iter=400, check_fe
         return zeros
     if check_feasibility and not is_feasible(A, rl, ru, xl, xu):
         return zeros
+    # gradient-based objective scaling (Ipopt's nlp_scaling_method default: max |grad| <= 100)
+    gmax = float(np.max(np.abs(q), initial=0.0))
+    fscale = 100.0 / gmax if gmax > 100.0 else 1.0
+    P_orig, q_orig = P, q
+    P = P * fscale
+    q = q * fscale
 
     # ---- eliminate fixed columns ------------------------------------------------
     fixed = xl == xu
@@ -342,6 +348,9 @@ def solve_qp(P, q, A, rl, ru, xl, xu, x0=None, tol=1e-10, max_iter=400, check_fe
     col_dual = np.zeros(n)
     col_dual[free] = zl[:nf] - zu[:nf]
     # reduced cost of eliminated (fixed) columns from stationarity
+    row_dual /= fscale
+    col_dual /= fscale
+    P, q = P_orig, q_orig
     if fixed.any():
         g = P @ x + q - A.T @ row_dual
         col_dual[fixed] = g[fixed]

@@ -1,0 +1,318 @@
+"""ctypes binding of ``include/sqpqp.h`` (the C-ABI of ``csrc/libsqpqp.so``).
+
+This is what the Python host mirror and the tests call; the Julia shim binds the
+very same symbols with ``ccall`` (julia/SqpQpB200.jl).  There is no fallback: if
+the shared library is missing the import of :func:`lib` raises, and every compute
+call needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libsqpqp.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "sqpqp.h")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--expt-extended-lambda", "-shared", "-Xcompiler", "-fPIC",
+]
+
+# MOI.TerminationStatusCode integers (include/sqpqp.h)
+MOI_OPTIMAL = 1
+MOI_INFEASIBLE = 2
+MOI_LOCALLY_SOLVED = 4
+MOI_LOCALLY_INFEASIBLE = 5
+MOI_ALMOST_LOCALLY_SOLVED = 10
+MOI_ITERATION_LIMIT = 11
+MOI_NUMERICAL_ERROR = 20
+MOI_NAMES = {
+    0: "OPTIMIZE_NOT_CALLED", 1: "OPTIMAL", 2: "INFEASIBLE", 4: "LOCALLY_SOLVED", 5: "LOCALLY_INFEASIBLE",
+    10: "ALMOST_LOCALLY_SOLVED", 11: "ITERATION_LIMIT", 20: "NUMERICAL_ERROR",
+}
+PHASE_QP, PHASE_FR, PHASE_SOC, PHASE_LP = 0, 1, 2, 3
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("moi_status", C.c_int32), ("admm_iters", C.c_int32), ("cg_iters", C.c_int32), ("polish_tries", C.c_int32),
+        ("polish_cg_iters", C.c_int32), ("polished", C.c_int32), ("rho_updates", C.c_int32), ("checks", C.c_int32),
+        ("rho", C.c_double), ("rho_box_floor", C.c_double), ("res_prim", C.c_double), ("res_dual", C.c_double),
+        ("objective", C.c_double),
+    ]
+
+
+INFO_DTYPE = np.dtype([
+    ("moi_status", "<i4"), ("admm_iters", "<i4"), ("cg_iters", "<i4"), ("polish_tries", "<i4"),
+    ("polish_cg_iters", "<i4"), ("polished", "<i4"), ("rho_updates", "<i4"), ("checks", "<i4"),
+    ("rho", "<f8"), ("rho_box_floor", "<f8"), ("res_prim", "<f8"), ("res_dual", "<f8"), ("objective", "<f8"),
+])
+assert INFO_DTYPE.itemsize == C.sizeof(Info)
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("rho0", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double),
+        ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("eps_inf", C.c_double),
+        ("rho_eq_mult", C.c_double), ("rho_min", C.c_double), ("rho_max", C.c_double), ("adapt_tol", C.c_double),
+        ("cg_rel0", C.c_double), ("rb_full_mult", C.c_double),
+        ("polish_trigger", C.c_double), ("polish_rho", C.c_double), ("polish_tol", C.c_double),
+        ("feas_tol", C.c_double), ("dual_tol", C.c_double),
+        ("max_iter", C.c_int32), ("check_every", C.c_int32), ("ruiz_iters", C.c_int32), ("cg_max", C.c_int32),
+        ("eig_iters", C.c_int32), ("polish_outer", C.c_int32), ("polish_cg_max", C.c_int32),
+        ("warm_start", C.c_int32), ("team", C.c_int32), ("threads", C.c_int32),
+    ]
+
+
+EXPORTS = [
+    "sqpqp_create", "sqpqp_destroy", "sqpqp_last_error", "sqpqp_default_options", "sqpqp_set_options", "sqpqp_stream",
+    "sqpqp_setup_nlp", "sqpqp_update_nlp", "sqpqp_update_nlp_device", "sqpqp_solve_tr", "sqpqp_num_slacks",
+    "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
+    "sqpqp_launch_count", "sqpqp_last_solve_ms",
+]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/sqpqp.cu for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [HEADER]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "sqpqp.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+def lib():
+    """Load libsqpqp.so (must have been built: ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the engine has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.sqpqp_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.sqpqp_destroy.argtypes = [vp]
+    L.sqpqp_last_error.argtypes = [vp]
+    L.sqpqp_last_error.restype = C.c_char_p
+    L.sqpqp_default_options.argtypes = [C.POINTER(Options)]
+    L.sqpqp_default_options.restype = None
+    L.sqpqp_set_options.argtypes = [vp, C.POINTER(Options)]
+    L.sqpqp_stream.argtypes = [vp]
+    L.sqpqp_stream.restype = vp
+    L.sqpqp_setup_nlp.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _lp, _lp, C.c_int64, _lp, _lp,
+                                  _dp, _dp, _dp, _dp, C.c_int32]
+    L.sqpqp_update_nlp.argtypes = [vp, _dp, _dp, _dp, _dp]
+    L.sqpqp_update_nlp_device.argtypes = [vp, vp, vp, vp, vp]
+    L.sqpqp_solve_tr.argtypes = [vp, C.c_int32, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _ip, C.c_void_p]
+    L.sqpqp_num_slacks.argtypes = [vp, _ip]
+    L.sqpqp_merit.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp]
+    L.sqpqp_kt_residuals.argtypes = [vp, _dp, _dp, _dp, _dp]
+    L.sqpqp_jac_times.argtypes = [vp, _dp, _dp]
+    L.sqpqp_get_csr.argtypes = [vp, C.c_int32, C.c_int32, _lp, _ip, _ip, _dp]
+    L.sqpqp_qp_setup.argtypes = [vp, C.c_int32, C.c_int32, C.c_int64, _lp, _lp, C.c_int64, _lp, _lp]
+    L.sqpqp_qp_solve.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, C.c_void_p]
+    L.sqpqp_launch_count.argtypes = [vp]
+    L.sqpqp_launch_count.restype = C.c_int64
+    L.sqpqp_last_solve_ms.argtypes = [vp]
+    L.sqpqp_last_solve_ms.restype = C.c_double
+    for name in EXPORTS:
+        f = getattr(L, name)
+        if f.restype is C.c_int:  # default restype
+            f.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def _l(a):
+    return None if a is None else a.ctypes.data_as(_lp)
+
+
+def _f64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+class SqpQpError(RuntimeError):
+    pass
+
+
+class Engine:
+    """Thin object wrapper over one ``sqpqp_handle`` (one GPU, one stream)."""
+
+    def __init__(self, device: int = 0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        rc = self.L.sqpqp_create(C.byref(self.h), device)
+        if rc != 0:
+            raise SqpQpError(f"sqpqp_create failed with {rc} (no CUDA device {device}? the engine has no CPU fallback)")
+        self.opts = Options()
+        self.L.sqpqp_default_options(C.byref(self.opts))
+        self.batch = self.n = self.m = self.S = 0
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.L.sqpqp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SqpQpError(f"sqpqp error {rc}: {self.L.sqpqp_last_error(self.h).decode()}")
+
+    def set_options(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.opts, k):
+                raise KeyError(k)
+            setattr(self.opts, k, v)
+        self._ck(self.L.sqpqp_set_options(self.h, C.byref(self.opts)))
+
+    # ---- NLP lane --------------------------------------------------------------
+    def setup_nlp(self, n, m, m_lin, j_row, j_col, h_row, h_col, x_L, x_U, g_L, g_U, batch=1):
+        j_row = np.ascontiguousarray(j_row, dtype=np.int64)
+        j_col = np.ascontiguousarray(j_col, dtype=np.int64)
+        h_row = np.ascontiguousarray(h_row if h_row is not None else [], dtype=np.int64)
+        h_col = np.ascontiguousarray(h_col if h_col is not None else [], dtype=np.int64)
+        x_L, x_U, g_L, g_U = (_f64(a) for a in (x_L, x_U, g_L, g_U))
+        per = int(g_L.ndim == 2 or x_L.ndim == 2)
+        if per:
+            x_L = np.ascontiguousarray(np.broadcast_to(x_L, (batch, n)))
+            x_U = np.ascontiguousarray(np.broadcast_to(x_U, (batch, n)))
+            g_L = np.ascontiguousarray(np.broadcast_to(g_L, (batch, m)))
+            g_U = np.ascontiguousarray(np.broadcast_to(g_U, (batch, m)))
+        self._ck(self.L.sqpqp_setup_nlp(self.h, batch, n, m, m_lin, j_row.shape[0], _l(j_row), _l(j_col), h_row.shape[0],
+                                        _l(h_row), _l(h_col), _d(x_L), _d(x_U), _d(g_L), _d(g_U), per))
+        self.batch, self.n, self.m = batch, n, m
+        self.nnz_j, self.nnz_h = j_row.shape[0], h_row.shape[0]
+        s = C.c_int32()
+        self._ck(self.L.sqpqp_num_slacks(self.h, C.byref(s)))
+        self.S = s.value
+
+    def update_nlp(self, dE, h_val, df, E):
+        B = self.batch
+        dE = _f64(dE).reshape(B, self.nnz_j)
+        h_val = _f64(h_val).reshape(B, self.nnz_h) if self.nnz_h else None
+        df = _f64(df).reshape(B, self.n)
+        E = _f64(E).reshape(B, self.m)
+        self._ck(self.L.sqpqp_update_nlp(self.h, _d(dE), _d(h_val), _d(df), _d(E)))
+
+    def update_nlp_device(self, dE_ptr, h_val_ptr, df_ptr, E_ptr):
+        self._ck(self.L.sqpqp_update_nlp_device(self.h, dE_ptr, h_val_ptr, df_ptr, E_ptr))
+
+    def solve_tr(self, phase, x_k, delta, E_override=None, active=None):
+        B, n, m, S = self.batch, self.n, self.m, self.S
+        x_k = _f64(x_k).reshape(B, n)
+        delta = np.ascontiguousarray(np.broadcast_to(np.asarray(delta, dtype=np.float64), (B,)))
+        E_override = _f64(E_override).reshape(B, m) if E_override is not None else None
+        act = np.ascontiguousarray(active, dtype=np.int32).reshape(B) if active is not None else None
+        p = np.zeros((B, n))
+        lam = np.zeros((B, m))
+        mxL = np.zeros((B, n))
+        mxU = np.zeros((B, n))
+        slack = np.zeros((B, max(S, 1)))
+        status = np.zeros(B, dtype=np.int32)
+        info = np.zeros(B, dtype=INFO_DTYPE)
+        self._ck(self.L.sqpqp_solve_tr(self.h, phase, _d(x_k), _d(delta), _d(E_override), _i(act), _d(p), _d(lam), _d(mxL),
+                                       _d(mxU), _d(slack), _i(status), info.ctypes.data_as(C.c_void_p)))
+        return p, lam, mxL, mxU, slack[:, :S], status, info
+
+    def merit(self, x, p, E_trial, f_trial, mu, fr=None):
+        B, n, m = self.batch, self.n, self.m
+        x = _f64(x).reshape(B, n)
+        p = _f64(p).reshape(B, n)
+        E_trial = _f64(E_trial).reshape(B, m)
+        f_trial = np.ascontiguousarray(np.broadcast_to(np.asarray(f_trial, dtype=np.float64), (B,)))
+        mu = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, dtype=np.float64), (B,)))
+        frv = np.ascontiguousarray(np.broadcast_to(np.asarray(fr, dtype=np.int32), (B,))) if fr is not None else None
+        out = [np.zeros(B) for _ in range(5)]
+        self._ck(self.L.sqpqp_merit(self.h, _d(x), _d(p), _d(E_trial), _d(f_trial), _d(mu), _i(frv), *[_d(o) for o in out]))
+        return dict(viol0=out[0], viol_trial=out[1], phi_trial=out[2], q0=out[3], qk=out[4])
+
+    def kt_residuals(self, lam, mult_x_U, mult_x_L):
+        B, n, m = self.batch, self.n, self.m
+        lam = _f64(lam).reshape(B, m)
+        mxU = _f64(mult_x_U).reshape(B, n)
+        mxL = _f64(mult_x_L).reshape(B, n)
+        kt = np.zeros(B)
+        self._ck(self.L.sqpqp_kt_residuals(self.h, _d(lam), _d(mxU), _d(mxL), _d(kt)))
+        return kt
+
+    def jac_times(self, p):
+        p = _f64(p).reshape(self.batch, self.n)
+        out = np.zeros((self.batch, self.m))
+        self._ck(self.L.sqpqp_jac_times(self.h, _d(p), _d(out)))
+        return out
+
+    def get_csr(self, which, b=0):
+        nnz = C.c_int64()
+        self._ck(self.L.sqpqp_get_csr(self.h, which, b, C.byref(nnz), None, None, None))
+        nrows = self.m if which == 0 else self.n
+        rp = np.zeros(nrows + 1, dtype=np.int32)
+        ci = np.zeros(max(nnz.value, 1), dtype=np.int32)
+        va = np.zeros(max(nnz.value, 1))
+        self._ck(self.L.sqpqp_get_csr(self.h, which, b, C.byref(nnz), _i(rp), _i(ci), _d(va)))
+        return rp, ci[: nnz.value], va[: nnz.value]
+
+    # ---- generic lane ----------------------------------------------------------
+    def qp_setup(self, nv, nc, p_row, p_col, a_row, a_col):
+        p_row = np.ascontiguousarray(p_row, dtype=np.int64)
+        p_col = np.ascontiguousarray(p_col, dtype=np.int64)
+        a_row = np.ascontiguousarray(a_row, dtype=np.int64)
+        a_col = np.ascontiguousarray(a_col, dtype=np.int64)
+        self._ck(self.L.sqpqp_qp_setup(self.h, nv, nc, p_row.shape[0], _l(p_row), _l(p_col), a_row.shape[0], _l(a_row), _l(a_col)))
+        self.batch, self.n, self.m, self.S = 1, nv, nc, 0
+        self.nnz_j, self.nnz_h = a_row.shape[0], p_row.shape[0]
+
+    def qp_solve(self, p_val, q, a_val, rl, ru, cl, cu):
+        x = np.zeros(self.n)
+        rd = np.zeros(max(self.m, 1))
+        cd = np.zeros(self.n)
+        st = C.c_int32()
+        info = np.zeros(1, dtype=INFO_DTYPE)
+        self._ck(self.L.sqpqp_qp_solve(self.h, _d(_f64(p_val)), _d(_f64(q)), _d(_f64(a_val)), _d(_f64(rl)), _d(_f64(ru)),
+                                       _d(_f64(cl)), _d(_f64(cu)), _d(x), _d(rd), _d(cd), C.byref(st),
+                                       info.ctypes.data_as(C.c_void_p)))
+        return x, rd[: self.m], cd, st.value, info[0]
+
+    @property
+    def launch_count(self):
+        return int(self.L.sqpqp_launch_count(self.h))
+
+    @property
+    def last_solve_ms(self):
+        return float(self.L.sqpqp_last_solve_ms(self.h))

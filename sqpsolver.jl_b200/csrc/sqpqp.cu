@@ -1,0 +1,710 @@
+// sqpqp.cu -- C ABI (include/sqpqp.h) of the B200-native QP-subproblem engine.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+//
+// Host side of the boundary: handle/stream/arena management, pinned staging for the
+// per-iteration value upload, the one-time device pattern build (K1) and kernel launches.
+// There is deliberately NO CPU implementation of any numerical step here: every entry point
+// that computes launches a kernel on the handle's stream.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <limits>
+
+#include "common.cuh"
+#include "pattern.cuh"
+#include "admm.cuh"
+#include "merit.cuh"
+
+struct Pending {
+    const void* pin;
+    void* user;
+    size_t bytes;
+};
+
+struct sqpqp_handle_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    sqpqp_options opts;
+    bool setup_done = false, updated = false;
+    Prob P;
+    int64_t nnzJ_coo = 0, nnzH_coo = 0;
+    std::vector<void*> allocs;
+    // staging (pinned host + device mirror), bump-allocated per API call
+    char* pin = nullptr;
+    char* dstage = nullptr;
+    size_t stage_cap = 0, stage_off = 0;
+    std::vector<Pending> pending;
+    // scatter
+    ScatterJob jobJ{}, jobT{}, jobH{};
+    double *d_dE = nullptr, *d_hval = nullptr, *d_df = nullptr, *d_E = nullptr;  // owned copies
+    double *d_gL = nullptr, *d_gU = nullptr, *d_xL = nullptr, *d_xU = nullptr;
+    double *d_xk = nullptr, *d_delta = nullptr, *d_Eov = nullptr;
+    int* d_active = nullptr;
+    int64_t launches = 0;
+    double last_ms = 0.0;
+    int num_sms = 148, coop_blocks = 0;
+    std::vector<double> avg_row;  // avg row length of J(normal), J(ext), T, H
+    // generic-lane bookkeeping
+    bool generic = false;
+};
+
+static int fail(sqpqp_handle h, int code, const char* msg) {
+    if (h) h->err = msg;
+    return code;
+}
+static int fail_cuda(sqpqp_handle h, cudaError_t e, const char* what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %s at line %d: %s", cudaGetErrorString(e), line, what);
+    if (h) h->err = buf;
+    return (e == cudaErrorMemoryAllocation) ? SQPQP_E_NOMEM : SQPQP_E_CUDA;
+}
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+template <class T>
+static int dalloc(sqpqp_handle h, T** p, size_t count) {
+    if (count == 0) count = 1;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) return fail_cuda(h, e, "cudaMalloc", __LINE__);
+    e = cudaMemsetAsync(q, 0, count * sizeof(T), h->stream);
+    if (e != cudaSuccess) return fail_cuda(h, e, "cudaMemsetAsync", __LINE__);
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+#define DALLOC(ptr, count)                                  \
+    do {                                                    \
+        int rc__ = dalloc(h, &(ptr), (size_t)(count));      \
+        if (rc__) return rc__;                              \
+    } while (0)
+
+static int ensure_stage(sqpqp_handle h, size_t bytes) {
+    bytes += 4096;
+    if (bytes > h->stage_cap) {
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        if (h->pin) cudaFreeHost(h->pin);
+        if (h->dstage) cudaFree(h->dstage);
+        h->pin = nullptr;
+        h->dstage = nullptr;
+        size_t cap = bytes + bytes / 4;
+        CUDA_OK(cudaMallocHost((void**)&h->pin, cap));
+        CUDA_OK(cudaMalloc((void**)&h->dstage, cap));
+        h->stage_cap = cap;
+    }
+    h->stage_off = 0;
+    h->pending.clear();
+    return 0;
+}
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// host -> pinned -> device (async).  Returns device pointer inside the staging mirror.
+template <class T>
+static const T* upload(sqpqp_handle h, const T* src, size_t count) {
+    if (!src || count == 0) return nullptr;
+    size_t bytes = count * sizeof(T);
+    size_t off = h->stage_off;
+    h->stage_off = align256(off + bytes);
+    memcpy(h->pin + off, src, bytes);
+    cudaMemcpyAsync(h->dstage + off, h->pin + off, bytes, cudaMemcpyHostToDevice, h->stream);
+    return (const T*)(h->dstage + off);
+}
+// device -> pinned (async) and remember the final host copy
+template <class T>
+static void download(sqpqp_handle h, const T* dsrc, T* user, size_t count) {
+    if (!user || count == 0) return;
+    size_t bytes = count * sizeof(T);
+    size_t off = h->stage_off;
+    h->stage_off = align256(off + bytes);
+    cudaMemcpyAsync(h->pin + off, dsrc, bytes, cudaMemcpyDeviceToHost, h->stream);
+    h->pending.push_back(Pending{h->pin + off, user, bytes});
+}
+static int finish(sqpqp_handle h) {
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    for (auto& p : h->pending) memcpy(p.user, p.pin, p.bytes);
+    h->pending.clear();
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int grid_for(int64_t work, int threads) {
+    int64_t g = (work + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > 148 * 16) g = 148 * 16;
+    return (int)g;
+}
+static int lg_lanes(double avg) {
+    int lg = 0;
+    while ((1 << lg) < avg && lg < 5) ++lg;
+    return lg;
+}
+
+// ---- K1 driver ---------------------------------------------------------------------------
+struct Pattern {
+    int nrows = 0, nslots = 0, Lv = 0;
+    int *row_ptr = nullptr, *col_idx = nullptr, *seg_ptr = nullptr, *seg_src = nullptr;
+};
+static int build_pattern(sqpqp_handle h, int L, const int* erow, const int* ecol, const int* esrc, int nrows, Pattern* out) {
+    int *cnt, *rstart, *cursor, *tcol, *tent, *scol, *sent, *head, *slotof;
+    DALLOC(cnt, nrows + 1);
+    DALLOC(rstart, nrows + 1);
+    DALLOC(cursor, nrows + 1);
+    DALLOC(tcol, L);
+    DALLOC(tent, L);
+    DALLOC(scol, L);
+    DALLOC(sent, L);
+    DALLOC(head, L + 1);
+    DALLOC(slotof, L + 2);
+    DALLOC(out->row_ptr, nrows + 1);
+    DALLOC(out->col_idx, L);
+    DALLOC(out->seg_ptr, L + 1);
+    DALLOC(out->seg_src, L);
+    const int TB = 256;
+    if (L > 0) {
+        k_count_rows<<<grid_for(L, TB), TB, 0, h->stream>>>(L, erow, cnt);
+        k_exscan<<<1, 1024, 0, h->stream>>>(nrows, cnt, rstart);
+        k_bucket<<<grid_for(L, TB), TB, 0, h->stream>>>(L, erow, ecol, rstart, cursor, tcol, tent);
+        k_sort_rows<<<grid_for((int64_t)nrows * 32, TB), TB, 0, h->stream>>>(nrows, rstart, tcol, tent, scol, sent);
+        k_heads<<<grid_for(nrows, TB), TB, 0, h->stream>>>(nrows, rstart, scol, head);
+        h->launches += 5;
+    } else {
+        k_exscan<<<1, 1024, 0, h->stream>>>(nrows, cnt, rstart);
+        h->launches += 1;
+    }
+    int Lv = 0;
+    CUDA_OK(cudaMemcpyAsync(&Lv, rstart + nrows, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    k_exscan<<<1, 1024, 0, h->stream>>>(Lv, head, slotof);
+    k_emit<<<grid_for(Lv > nrows ? Lv : nrows + 1, TB), TB, 0, h->stream>>>(nrows, Lv, rstart, scol, sent, esrc, head, slotof,
+                                                                         out->row_ptr, out->col_idx, out->seg_ptr,
+                                                                         out->seg_src);
+    h->launches += 2;
+    int ns = 0;
+    CUDA_OK(cudaMemcpyAsync(&ns, slotof + Lv, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaGetLastError());
+    out->nrows = nrows;
+    out->nslots = ns;
+    out->Lv = Lv;
+    return 0;
+}
+
+// ---- lifecycle -------------------------------------------------------------------------
+extern "C" void sqpqp_default_options(sqpqp_options* o) {
+    o->rho0 = 0.1; o->sigma = 1e-6; o->alpha = 1.6;
+    o->eps_abs = 1e-7; o->eps_rel = 1e-7; o->eps_inf = 1e-6;
+    o->rho_eq_mult = 1e3; o->rho_min = 1e-6; o->rho_max = 1e6; o->adapt_tol = 3.0;
+    o->cg_rel0 = 0.2;
+    o->rb_full_mult = 1.5;
+    o->polish_trigger = 5e-2; o->polish_rho = 1e4; o->polish_tol = 1e-11; o->feas_tol = 1e-9; o->dual_tol = 1e-9;
+    o->max_iter = 6000; o->check_every = 25; o->ruiz_iters = 15; o->cg_max = 300; o->eig_iters = 60;
+    o->polish_outer = 20; o->polish_cg_max = 3000;
+    o->warm_start = 1; o->team = 0; o->threads = 0;
+}
+
+extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
+    if (!out) return SQPQP_E_BADARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SQPQP_E_CUDA;
+    sqpqp_handle h = new (std::nothrow) sqpqp_handle_s();
+    if (!h) return SQPQP_E_NOMEM;
+    h->device = device;
+    memset(&h->P, 0, sizeof(Prob));
+    sqpqp_default_options(&h->opts);
+    DeviceGuard g(device);
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        delete h;
+        return SQPQP_E_CUDA;
+    }
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    *out = h;
+    return 0;
+}
+
+static void free_problem(sqpqp_handle h) {
+    cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    memset(&h->P, 0, sizeof(Prob));
+    h->setup_done = h->updated = false;
+}
+
+extern "C" int sqpqp_destroy(sqpqp_handle h) {
+    if (!h) return SQPQP_E_BADARG;
+    DeviceGuard g(h->device);
+    free_problem(h);
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->dstage) cudaFree(h->dstage);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" const char* sqpqp_last_error(sqpqp_handle h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" void* sqpqp_stream(sqpqp_handle h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int64_t sqpqp_launch_count(sqpqp_handle h) { return h ? h->launches : 0; }
+extern "C" double sqpqp_last_solve_ms(sqpqp_handle h) { return h ? h->last_ms : 0.0; }
+
+extern "C" int sqpqp_set_options(sqpqp_handle h, const sqpqp_options* o) {
+    if (!h || !o) return SQPQP_E_BADARG;
+    if (o->threads < 0 || o->threads > 256 || (o->threads % 32) != 0) return fail(h, SQPQP_E_BADARG, "threads must be a multiple of 32 in [0,256]");
+    if (o->check_every < 1 || o->max_iter < 1 || !(o->rho0 > 0) || !(o->alpha > 0 && o->alpha < 2)) return fail(h, SQPQP_E_BADARG, "bad option value");
+    h->opts = *o;
+    return 0;
+}
+
+extern "C" int sqpqp_num_slacks(sqpqp_handle h, int32_t* S) {
+    if (!h || !S) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    *S = h->P.S;
+    return 0;
+}
+
+// ---- setup -------------------------------------------------------------------------------
+extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t m, int32_t m_lin, int64_t nnz_j,
+                               const int64_t* j_row, const int64_t* j_col, int64_t nnz_h, const int64_t* h_row,
+                               const int64_t* h_col, const double* x_L, const double* x_U, const double* g_L,
+                               const double* g_U, int32_t bounds_per_instance) {
+    if (!h) return SQPQP_E_BADARG;
+    if (batch < 1 || n < 1 || m < 0 || m_lin < 0 || m_lin > m || nnz_j < 0 || nnz_h < 0) return fail(h, SQPQP_E_BADARG, "bad sizes");
+    if ((nnz_j > 0 && (!j_row || !j_col)) || (nnz_h > 0 && (!h_row || !h_col)) || !x_L || !x_U || (m > 0 && (!g_L || !g_U)))
+        return fail(h, SQPQP_E_BADARG, "null pointer");
+    if (nnz_j + (int64_t)2 * m > std::numeric_limits<int>::max() / 4 || nnz_h > std::numeric_limits<int>::max() / 4)
+        return fail(h, SQPQP_E_BADARG, "nnz too large for int32 indexing");
+    for (int64_t k = 0; k < nnz_j; ++k)
+        if (j_row[k] < 1 || j_row[k] > m || j_col[k] < 1 || j_col[k] > n) return fail(h, SQPQP_E_BADARG, "Jacobian COO index out of range");
+    for (int64_t k = 0; k < nnz_h; ++k)
+        if (h_row[k] < 1 || h_row[k] > n || h_col[k] < 1 || h_col[k] > n) return fail(h, SQPQP_E_BADARG, "Hessian COO index out of range");
+    DeviceGuard g(h->device);
+    free_problem(h);
+    Prob& P = h->P;
+    P.n = n; P.m = m; P.mlin = m_lin; P.batch = batch;
+    P.has_hess = nnz_h > 0;
+    h->nnzJ_coo = nnz_j;
+    h->nnzH_coo = nnz_h;
+
+    // slack columns of create_model! (subproblem_JuMP.jl:59-65): rows > m_lin get u_i, and
+    // v_i when both bounds are finite; u enters with +1 except on pure <= rows (:110)
+    std::vector<int> srow;
+    std::vector<double> ssign;
+    for (int i = m_lin; i < m; ++i) {
+        bool lo = g_L[i] > -INFINITY, up = g_U[i] < INFINITY;
+        srow.push_back(i);
+        ssign.push_back((!lo && up) ? -1.0 : 1.0);
+        if (lo && up) {
+            srow.push_back(i);
+            ssign.push_back(-1.0);
+        }
+    }
+    const int S = (int)srow.size();
+    P.S = S;
+    P.Ne = n + S;
+
+    size_t stage = (size_t)(nnz_j + nnz_h) * 2 * sizeof(int64_t) + (size_t)S * 16 +
+                   ((size_t)2 * n + 2 * (size_t)m) * sizeof(double) * (bounds_per_instance ? batch : 1) + 16384;
+    int rc = ensure_stage(h, stage);
+    if (rc) return rc;
+    const int64_t* d_jr = upload(h, j_row, (size_t)nnz_j);
+    const int64_t* d_jc = upload(h, j_col, (size_t)nnz_j);
+    const int64_t* d_hr = upload(h, h_row, (size_t)nnz_h);
+    const int64_t* d_hc = upload(h, h_col, (size_t)nnz_h);
+    int* d_srow;
+    double* d_ssign;
+    DALLOC(d_srow, S);
+    DALLOC(d_ssign, S);
+    if (S) {
+        CUDA_OK(cudaMemcpyAsync(d_srow, upload(h, srow.data(), (size_t)S), S * sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_OK(cudaMemcpyAsync(d_ssign, upload(h, ssign.data(), (size_t)S), S * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    P.slack_row = d_srow;
+    P.slack_sign = d_ssign;
+
+    // K1: three patterns
+    const int LJ = (int)nnz_j + S, LH = 2 * (int)nnz_h;
+    int *erow, *ecol, *esrc;
+    DALLOC(erow, (LJ > LH ? LJ : LH));
+    DALLOC(ecol, (LJ > LH ? LJ : LH));
+    DALLOC(esrc, (LJ > LH ? LJ : LH));
+    Pattern pj, pt, ph;
+    const int TB = 256;
+    if (LJ > 0) {
+        k_entries_jac<<<grid_for(LJ, TB), TB, 0, h->stream>>>(nnz_j, d_jr, d_jc, S, d_srow, n, 0, erow, ecol, esrc);
+        h->launches++;
+    }
+    if ((rc = build_pattern(h, LJ, erow, ecol, esrc, m, &pj))) return rc;
+    if (LJ > 0) {
+        k_entries_jac<<<grid_for(LJ, TB), TB, 0, h->stream>>>(nnz_j, d_jr, d_jc, S, d_srow, n, 1, erow, ecol, esrc);
+        h->launches++;
+    }
+    if ((rc = build_pattern(h, LJ, erow, ecol, esrc, P.Ne, &pt))) return rc;
+    if (LH > 0) {
+        k_entries_hess<<<grid_for(nnz_h, TB), TB, 0, h->stream>>>(nnz_h, d_hr, d_hc, erow, ecol, esrc);
+        h->launches++;
+    }
+    if ((rc = build_pattern(h, LH, erow, ecol, esrc, n, &ph))) return rc;
+    int* re_n;
+    DALLOC(re_n, m + 1);
+    if (m > 0) {
+        k_row_end_normal<<<grid_for(m, TB), TB, 0, h->stream>>>(m, pj.row_ptr, pj.col_idx, n, re_n);
+        h->launches++;
+    }
+    P.J_rb = pj.row_ptr; P.J_re_e = pj.row_ptr + 1; P.J_re_n = re_n; P.J_col = pj.col_idx;
+    P.T_rb = pt.row_ptr; P.T_col = pt.col_idx;
+    P.H_rb = ph.row_ptr; P.H_col = ph.col_idx;
+    P.nnzJ = pj.nslots; P.nnzT = pt.nslots; P.nnzH = ph.nslots;
+    // lanes per row from the average row length of each matrix
+    double nnzJn = (double)(pj.nslots - S);
+    P.lgJn = lg_lanes(m ? nnzJn / m : 1.0);
+    P.lgJe = lg_lanes(m ? (double)pj.nslots / m : 1.0);
+    P.lgT = lg_lanes((double)pt.nslots / P.Ne);
+    P.lgH = lg_lanes(n ? (double)ph.nslots / n : 1.0);
+
+    // per-instance storage
+    const size_t B = batch;
+    DALLOC(P.Jv, B * P.nnzJ); DALLOC(P.Tv, B * P.nnzT); DALLOC(P.Hv, B * P.nnzH);
+    DALLOC(P.Jsv, B * P.nnzJ); DALLOC(P.Tsv, B * P.nnzT); DALLOC(P.Hsv, B * P.nnzH);
+    for (int k = 0; k < N_COUNT; ++k) DALLOC(P.nv[k], B * P.Ne);
+    for (int k = 0; k < M_COUNT; ++k) DALLOC(P.mv[k], B * (m > 0 ? m : 1));
+    DALLOC(P.codeC, B * (m > 0 ? m : 1)); DALLOC(P.prevC, B * (m > 0 ? m : 1)); DALLOC(P.triedC, B * (m > 0 ? m : 1));
+    DALLOC(P.codeB, B * P.Ne); DALLOC(P.prevB, B * P.Ne); DALLOC(P.triedB, B * P.Ne);
+    DALLOC(P.rho_w, B);
+    DALLOC(P.o_p, B * n); DALLOC(P.o_lam, B * (m > 0 ? m : 1)); DALLOC(P.o_mxL, B * n); DALLOC(P.o_mxU, B * n);
+    DALLOC(P.o_slack, B * (S > 0 ? S : 1));
+    DALLOC(P.o_info, B);
+    DALLOC(h->d_dE, B * (size_t)nnz_j); DALLOC(h->d_hval, B * (size_t)nnz_h); DALLOC(h->d_df, B * n); DALLOC(h->d_E, B * (m > 0 ? m : 1));
+    DALLOC(h->d_xk, B * n); DALLOC(h->d_delta, B); DALLOC(h->d_Eov, B * (m > 0 ? m : 1)); DALLOC(h->d_active, B);
+    const size_t nb = bounds_per_instance ? B : 1;
+    DALLOC(h->d_gL, nb * (m > 0 ? m : 1)); DALLOC(h->d_gU, nb * (m > 0 ? m : 1)); DALLOC(h->d_xL, nb * n); DALLOC(h->d_xU, nb * n);
+    CUDA_OK(cudaMemcpyAsync(h->d_xL, upload(h, x_L, nb * n), nb * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->d_xU, upload(h, x_U, nb * n), nb * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (m > 0) {
+        CUDA_OK(cudaMemcpyAsync(h->d_gL, upload(h, g_L, nb * m), nb * m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_OK(cudaMemcpyAsync(h->d_gU, upload(h, g_U, nb * m), nb * m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    P.gL = h->d_gL; P.gU = h->d_gU; P.xL = h->d_xL; P.xU = h->d_xU;
+    P.gstride = bounds_per_instance ? m : 0;
+    P.xstride = bounds_per_instance ? n : 0;
+    P.df = h->d_df; P.E = h->d_E; P.Eov = nullptr; P.xk = h->d_xk; P.delta = h->d_delta; P.active = nullptr;
+
+    // cooperative-grid scratch
+    int bps = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_solve_grid, 256, 0));
+    if (bps < 1) bps = 1;
+    if (bps > 2) bps = 2;
+    h->coop_blocks = bps * h->num_sms;
+    P.gred_stride = h->coop_blocks;
+    DALLOC(P.gred, (size_t)2 * SQPQP_MAX_RED * P.gred_stride);
+
+    // scatter jobs
+    h->jobJ = ScatterJob{P.nnzJ, (int)nnz_j, pj.seg_ptr, pj.seg_src, h->d_dE, d_ssign, P.Jv};
+    h->jobT = ScatterJob{P.nnzT, (int)nnz_j, pt.seg_ptr, pt.seg_src, h->d_dE, d_ssign, P.Tv};
+    h->jobH = ScatterJob{P.nnzH, (int)nnz_h, ph.seg_ptr, ph.seg_src, h->d_hval, nullptr, P.Hv};
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaGetLastError());
+    h->setup_done = true;
+    h->generic = false;
+    return 0;
+}
+
+// ---- update ------------------------------------------------------------------------------
+static int launch_scatter(sqpqp_handle h, const double* dE, const double* hval) {
+    ScatterJob a = h->jobJ, b = h->jobT, c = h->jobH;
+    a.vals = dE; b.vals = dE; c.vals = hval;
+    int64_t work = (int64_t)(a.nslots > b.nslots ? a.nslots : b.nslots) * h->P.batch;
+    k_scatter<<<grid_for(work, 256), 256, 0, h->stream>>>(a, b, c, h->P.batch);
+    h->launches++;
+    return 0;
+}
+
+extern "C" int sqpqp_update_nlp(sqpqp_handle h, const double* dE, const double* h_val, const double* df, const double* E) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    Prob& P = h->P;
+    if ((h->nnzJ_coo && !dE) || !df || (P.m && !E) || (h->nnzH_coo && !h_val)) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    const size_t B = P.batch;
+    size_t bytes = B * ((size_t)h->nnzJ_coo + h->nnzH_coo + P.n + P.m) * sizeof(double) + 8192;
+    int rc = ensure_stage(h, bytes);
+    if (rc) return rc;
+    // pinned staging -> async H2D straight into the owned device arrays
+    struct Cp { double* dst; const double* src; size_t cnt; } cps[4] = {
+        {h->d_dE, dE, B * (size_t)h->nnzJ_coo}, {h->d_hval, h_val, B * (size_t)h->nnzH_coo}, {h->d_df, df, B * P.n}, {h->d_E, E, B * P.m}};
+    for (auto& c : cps) {
+        if (!c.cnt) continue;
+        size_t off = h->stage_off;
+        h->stage_off = align256(off + c.cnt * sizeof(double));
+        memcpy(h->pin + off, c.src, c.cnt * sizeof(double));
+        CUDA_OK(cudaMemcpyAsync(c.dst, h->pin + off, c.cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    P.df = h->d_df; P.E = h->d_E;
+    launch_scatter(h, h->d_dE, h->d_hval);
+    // the pinned buffer is reused by the next call: wait for the copies (not for the scatter's consumers)
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaGetLastError());
+    h->updated = true;
+    return 0;
+}
+
+extern "C" int sqpqp_update_nlp_device(sqpqp_handle h, const double* dE, const double* h_val, const double* df, const double* E) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    Prob& P = h->P;
+    if ((h->nnzJ_coo && !dE) || !df || (P.m && !E) || (h->nnzH_coo && !h_val)) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    P.df = df; P.E = E;
+    launch_scatter(h, dE, h_val);
+    CUDA_OK(cudaGetLastError());
+    h->updated = true;
+    return 0;
+}
+
+// ---- solve -------------------------------------------------------------------------------
+static int pick_threads(sqpqp_handle h, int phase) {
+    if (h->opts.threads) return h->opts.threads;
+    int len = h->P.m > h->P.n ? h->P.m : h->P.n;
+    if (phase == SQPQP_PHASE_FR) len = h->P.m > h->P.Ne ? h->P.m : h->P.Ne;
+    int t = 64;
+    while (t < 256 && t * 2 <= len) t *= 2;
+    return t;
+}
+
+extern "C" int sqpqp_solve_tr(sqpqp_handle h, int32_t phase, const double* x_k, const double* delta, const double* E_override,
+                              const int32_t* active, double* p, double* lambda, double* mult_x_L, double* mult_x_U,
+                              double* slack, int32_t* moi_status, sqpqp_info* info) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
+    if (phase < 0 || phase > 3 || !x_k || !delta) return fail(h, SQPQP_E_BADARG, "bad phase or null pointer");
+    if (phase == SQPQP_PHASE_SOC && !E_override) return fail(h, SQPQP_E_BADARG, "SOC phase needs E_override");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    const size_t B = P.batch;
+    size_t bytes = B * ((size_t)3 * P.n + 2 * (size_t)P.m + P.S + 8) * sizeof(double) * 2 + B * (sizeof(sqpqp_info) + 16) + 16384;
+    int rc = ensure_stage(h, bytes);
+    if (rc) return rc;
+    for (size_t b = 0; b < B; ++b)
+        if (!(delta[b] > 0.0)) return fail(h, SQPQP_E_BADARG, "delta must be positive");
+    P.xk = upload(h, x_k, B * P.n);
+    P.delta = upload(h, delta, B);
+    P.Eov = (phase == SQPQP_PHASE_SOC) ? upload(h, E_override, B * P.m) : nullptr;
+    P.active = active ? upload(h, active, B) : nullptr;
+
+    DevOpts O{h->opts};
+    int team = h->opts.team;
+    if (team == 0) team = (B == 1 && (size_t)P.Ne + P.m > 6000) ? 2 : 1;
+    CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+    if (team == 2) {
+        void* args[] = {(void*)&P, (void*)&O, (void*)&phase};
+        CUDA_OK(cudaLaunchCooperativeKernel((void*)k_solve_grid, dim3(h->coop_blocks), dim3(256), args, 0, h->stream));
+    } else {
+        int threads = pick_threads(h, phase);
+        int grid = (int)(B < 65535 ? B : 65535);
+        k_solve_cta<<<grid, threads, 0, h->stream>>>(P, O, phase);
+    }
+    h->launches++;
+    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+    download(h, P.o_p, p, B * P.n);
+    download(h, P.o_lam, lambda, B * P.m);
+    download(h, P.o_mxL, mult_x_L, B * P.n);
+    download(h, P.o_mxU, mult_x_U, B * P.n);
+    download(h, P.o_slack, slack, B * P.S);
+    download(h, P.o_info, info, B);
+    std::vector<sqpqp_info> tmp;
+    if (moi_status && !info) {
+        tmp.resize(B);
+        download(h, P.o_info, tmp.data(), B);
+    }
+    rc = finish(h);
+    if (rc) return rc;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->last_ms = ms;
+    if (moi_status) {
+        const sqpqp_info* src = info ? info : tmp.data();
+        for (size_t b = 0; b < B; ++b) moi_status[b] = (!active || active[b]) ? src[b].moi_status : moi_status[b];
+    }
+    P.active = nullptr;
+    P.Eov = nullptr;
+    return 0;
+}
+
+// ---- merit / KT --------------------------------------------------------------------------
+extern "C" int sqpqp_merit(sqpqp_handle h, const double* x, const double* p, const double* E_trial, const double* f_trial,
+                           const double* mu, const int32_t* fr, double* viol0, double* viol_trial, double* phi_trial,
+                           double* q0, double* qk) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
+    if (!x || !p || !E_trial || !f_trial || !mu) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    const size_t B = P.batch;
+    int rc = ensure_stage(h, B * ((size_t)2 * P.n + P.m + 16) * sizeof(double) + 16384);
+    if (rc) return rc;
+    MeritArgs A;
+    A.x = upload(h, x, B * P.n);
+    A.p = upload(h, p, B * P.n);
+    A.Etrial = upload(h, E_trial, B * P.m);
+    A.ftrial = upload(h, f_trial, B);
+    A.mu = upload(h, mu, B);
+    A.fr = fr ? upload(h, fr, B) : nullptr;
+    double* out;  // 5 x B results in the (zeroed) N_TMP workspace of instance 0.. (batch*Ne >= 5*batch only if Ne>=5)
+    size_t off = h->stage_off;
+    h->stage_off = align256(off + 5 * B * sizeof(double));
+    out = (double*)(h->dstage + off);
+    A.viol0 = out; A.violt = out + B; A.phit = out + 2 * B; A.q0 = out + 3 * B; A.qk = out + 4 * B;
+    P.active = nullptr;
+    k_merit<<<(int)(B < 65535 ? B : 65535), 128, 0, h->stream>>>(P, A);
+    h->launches++;
+    download(h, A.viol0, viol0, B);
+    download(h, A.violt, viol_trial, B);
+    download(h, A.phit, phi_trial, B);
+    download(h, A.q0, q0, B);
+    download(h, A.qk, qk, B);
+    return finish(h);
+}
+
+extern "C" int sqpqp_kt_residuals(sqpqp_handle h, const double* lambda, const double* mult_x_U, const double* mult_x_L, double* kt) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
+    if (!lambda || !mult_x_U || !mult_x_L || !kt) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    const size_t B = P.batch;
+    int rc = ensure_stage(h, B * ((size_t)2 * P.n + P.m + 8) * sizeof(double) * 2 + 16384);
+    if (rc) return rc;
+    KtArgs A;
+    A.lam = upload(h, lambda, B * P.m);
+    A.mxU = upload(h, mult_x_U, B * P.n);
+    A.mxL = upload(h, mult_x_L, B * P.n);
+    size_t off = h->stage_off;
+    h->stage_off = align256(off + B * sizeof(double));
+    A.kt = (double*)(h->dstage + off);
+    P.active = nullptr;
+    k_kt<<<(int)(B < 65535 ? B : 65535), 128, 0, h->stream>>>(P, A);
+    h->launches++;
+    download(h, A.kt, kt, B);
+    return finish(h);
+}
+
+extern "C" int sqpqp_jac_times(sqpqp_handle h, const double* p, double* out) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
+    if (!p || !out) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    const size_t B = P.batch;
+    int rc = ensure_stage(h, B * ((size_t)P.n + 2 * (size_t)P.m + 8) * sizeof(double) + 16384);
+    if (rc) return rc;
+    const double* dp = upload(h, p, B * P.n);
+    size_t off = h->stage_off;
+    h->stage_off = align256(off + B * P.m * sizeof(double));
+    double* dout = (double*)(h->dstage + off);
+    k_jac_times<<<(int)(B < 65535 ? B : 65535), 128, 0, h->stream>>>(P, dp, dout);
+    h->launches++;
+    download(h, dout, out, B * P.m);
+    return finish(h);
+}
+
+// ---- read-back of the device matrices (parity tests) ----------------------------------------
+extern "C" int sqpqp_get_csr(sqpqp_handle h, int32_t which, int32_t b, int64_t* nnz, int32_t* row_ptr, int32_t* col_idx, double* values) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    Prob& P = h->P;
+    if (which < 0 || which > 2 || b < 0 || b >= P.batch) return fail(h, SQPQP_E_BADARG, "bad selector");
+    DeviceGuard g(h->device);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    int nrows = which == 0 ? P.m : P.n;
+    const int* rb = which == 0 ? P.J_rb : (which == 1 ? P.T_rb : P.H_rb);
+    const int* col = which == 0 ? P.J_col : (which == 1 ? P.T_col : P.H_col);
+    const double* val = which == 0 ? P.Jv + (size_t)b * P.nnzJ : (which == 1 ? P.Tv + (size_t)b * P.nnzT : P.Hv + (size_t)b * P.nnzH);
+    std::vector<int> rp(nrows + 1);
+    CUDA_OK(cudaMemcpy(rp.data(), rb, (nrows + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    if (which == 0) {
+        // strip the slack columns: row i keeps [rb[i], re_n[i])
+        std::vector<int> ren(nrows);
+        if (nrows) CUDA_OK(cudaMemcpy(ren.data(), P.J_re_n, nrows * sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<int> c(P.nnzJ);
+        std::vector<double> v(P.nnzJ);
+        if (P.nnzJ) {
+            CUDA_OK(cudaMemcpy(c.data(), col, P.nnzJ * sizeof(int), cudaMemcpyDeviceToHost));
+            CUDA_OK(cudaMemcpy(v.data(), val, P.nnzJ * sizeof(double), cudaMemcpyDeviceToHost));
+        }
+        int64_t cnt = 0;
+        for (int i = 0; i < nrows; ++i) {
+            if (row_ptr) row_ptr[i] = (int32_t)cnt;
+            for (int k = rp[i]; k < ren[i]; ++k, ++cnt) {
+                if (col_idx) col_idx[cnt] = c[k];
+                if (values) values[cnt] = v[k];
+            }
+        }
+        if (row_ptr) row_ptr[nrows] = (int32_t)cnt;
+        if (nnz) *nnz = cnt;
+        return 0;
+    }
+    int64_t cnt = rp[nrows];
+    if (nnz) *nnz = cnt;
+    if (row_ptr) memcpy(row_ptr, rp.data(), (nrows + 1) * sizeof(int));
+    if (col_idx && cnt) CUDA_OK(cudaMemcpy(col_idx, col, cnt * sizeof(int), cudaMemcpyDeviceToHost));
+    if (values && cnt) CUDA_OK(cudaMemcpy(values, val, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- generic QP lane ------------------------------------------------------------------------
+extern "C" int sqpqp_qp_setup(sqpqp_handle h, int32_t nv, int32_t nc, int64_t nnz_p, const int64_t* p_row, const int64_t* p_col,
+                              int64_t nnz_a, const int64_t* a_row, const int64_t* a_col) {
+    if (!h) return SQPQP_E_BADARG;
+    if (nv < 1 || nc < 0) return fail(h, SQPQP_E_BADARG, "bad sizes");
+    // bounds are supplied per solve; setup only needs finiteness for slack columns, and with
+    // m_lin = nc there are none.
+    std::vector<double> lo((size_t)(nv > nc ? nv : nc), -INFINITY), hi((size_t)(nv > nc ? nv : nc), INFINITY);
+    int rc = sqpqp_setup_nlp(h, 1, nv, nc, nc, nnz_a, a_row, a_col, nnz_p, p_row, p_col, lo.data(), hi.data(), lo.data(), hi.data(), 0);
+    if (rc) return rc;
+    h->generic = true;
+    return 0;
+}
+
+extern "C" int sqpqp_qp_solve(sqpqp_handle h, const double* p_val, const double* q, const double* a_val, const double* rl,
+                              const double* ru, const double* cl, const double* cu, double* x, double* row_dual,
+                              double* col_dual, int32_t* moi_status, sqpqp_info* info) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->generic) return fail(h, SQPQP_E_STATE, "qp_setup not called");
+    Prob& P = h->P;
+    if (!q || !cl || !cu || (P.m && (!rl || !ru))) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    // bounds
+    int rc = ensure_stage(h, ((size_t)2 * P.n + 2 * (size_t)P.m) * sizeof(double) + 8192);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(h->d_xL, upload(h, cl, (size_t)P.n), P.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->d_xU, upload(h, cu, (size_t)P.n), P.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (P.m) {
+        CUDA_OK(cudaMemcpyAsync(h->d_gL, upload(h, rl, (size_t)P.m), P.m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_OK(cudaMemcpyAsync(h->d_gU, upload(h, ru, (size_t)P.m), P.m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    std::vector<double> zeros((size_t)(P.n > P.m ? P.n : P.m), 0.0);
+    rc = sqpqp_update_nlp(h, a_val, p_val, q, zeros.data());
+    if (rc) return rc;
+    double delta = INFINITY;
+    std::vector<double> mxL(P.n), mxU(P.n);
+    int32_t st = 0;
+    rc = sqpqp_solve_tr(h, SQPQP_PHASE_QP, zeros.data(), &delta, nullptr, nullptr, x, row_dual, mxL.data(), mxU.data(), nullptr, &st, info);
+    if (rc) return rc;
+    if (col_dual)
+        for (int j = 0; j < P.n; ++j) col_dual[j] = mxL[j] + mxU[j];
+    if (moi_status) *moi_status = st;
+    return 0;
+}
