@@ -67,6 +67,8 @@ typedef struct sqpqp_info {
     int32_t polished;        /* 1: returned point is the verified active-set (KKT) refinement */
     int32_t rho_updates;
     int32_t checks;          /* residual checks (3 SpMV each) */
+    int32_t ipm_iters;       /* interior-point iterations (0 if the ADMM path solved it) */
+    int32_t chol_factorizations; /* sparse Cholesky factorisations of the condensed Newton matrix */
     double rho;              /* final ADMM step size (scaled space) */
     double rho_box_floor;    /* 1.5*|lambda_min(P_scaled)| -- nonconvexity guard, 0 if P >= 0 */
     double res_prim;         /* unscaled inf-norm primal residual of the returned point */
@@ -85,7 +87,14 @@ typedef struct sqpqp_options {
     int32_t max_iter, check_every, ruiz_iters, cg_max, eig_iters, polish_outer, polish_cg_max;
     int32_t warm_start;      /* 1: start ADMM from the previous solve's (p, y) of the same instance */
     int32_t team;            /* 0 auto, 1 one CTA per instance, 2 whole grid per instance (cooperative) */
-    int32_t threads;         /* CTA size (multiple of 32); 0 = auto */
+    int32_t threads;         /* CTA size (multiple of 32, <= 512); 0 = auto */
+    int32_t method;          /* 0 auto: interior point (Cholesky) with ADMM fallback; 1 ADMM only; 2 interior point only */
+    int32_t ipm_max_iter;
+    int32_t fallback_max_iter; /* ADMM iteration cap when it runs as the fallback of a failed interior-point solve */
+    double ipm_eps, ipm_delta0, ipm_delta_min, ipm_rho0, ipm_tau, ipm_mu0, ipm_mu_min, ipm_kappa_eps;
+    int32_t ipm_refine;      /* iterative-refinement steps per Newton solve */
+    int32_t verbose;         /* 1: device printf of the interior-point iterations (debugging) */
+    int32_t smem_kb;         /* shared-memory budget per CTA for resident scratch arrays; -1 = auto, 0 = none */
 } sqpqp_options;
 
 /* ---- lifecycle ------------------------------------------------------------------ */
@@ -136,6 +145,19 @@ int sqpqp_solve_tr(sqpqp_handle h, int32_t phase, const double* x_k, const doubl
                    const double* E_override, const int32_t* active,
                    double* p, double* lambda, double* mult_x_L, double* mult_x_U, double* slack,
                    int32_t* moi_status, sqpqp_info* info);
+/* Device-pointer variant for a device-side evaluator / graph of solves: all arguments are
+ * DEVICE pointers, nothing is copied, the call does not block.  Results stay in the handle's
+ * device buffers (sqpqp_device_outputs); sqpqp_sync waits for the stream; sqpqp_fetch_info
+ * copies only the per-instance info records back. */
+int sqpqp_solve_tr_device(sqpqp_handle h, int32_t phase, const double* x_k, const double* delta,
+                          const double* E_override, const int32_t* active);
+int sqpqp_sync(sqpqp_handle h);
+int sqpqp_device_outputs(sqpqp_handle h, double** p, double** lambda, double** mult_x_L, double** mult_x_U,
+                         sqpqp_info** info);
+int sqpqp_fetch_info(sqpqp_handle h, sqpqp_info* info);
+/* Size of the shared symbolic Cholesky factor of the condensed Newton matrix (0 if unavailable):
+ * nnz(L), elimination-tree levels, flops per numeric factorisation. */
+int sqpqp_chol_stats(sqpqp_handle h, int64_t* nnzL, int64_t* nlev, int64_t* flops);
 /* Number of slack columns S (order: for each row i > m_lin: u_i, then v_i if two-sided). */
 int sqpqp_num_slacks(sqpqp_handle h, int32_t* S);
 

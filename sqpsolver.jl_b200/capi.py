@@ -43,6 +43,7 @@ class Info(C.Structure):
     _fields_ = [
         ("moi_status", C.c_int32), ("admm_iters", C.c_int32), ("cg_iters", C.c_int32), ("polish_tries", C.c_int32),
         ("polish_cg_iters", C.c_int32), ("polished", C.c_int32), ("rho_updates", C.c_int32), ("checks", C.c_int32),
+        ("ipm_iters", C.c_int32), ("chol_factorizations", C.c_int32),
         ("rho", C.c_double), ("rho_box_floor", C.c_double), ("res_prim", C.c_double), ("res_dual", C.c_double),
         ("objective", C.c_double),
     ]
@@ -51,6 +52,7 @@ class Info(C.Structure):
 INFO_DTYPE = np.dtype([
     ("moi_status", "<i4"), ("admm_iters", "<i4"), ("cg_iters", "<i4"), ("polish_tries", "<i4"),
     ("polish_cg_iters", "<i4"), ("polished", "<i4"), ("rho_updates", "<i4"), ("checks", "<i4"),
+    ("ipm_iters", "<i4"), ("chol_factorizations", "<i4"),
     ("rho", "<f8"), ("rho_box_floor", "<f8"), ("res_prim", "<f8"), ("res_dual", "<f8"), ("objective", "<f8"),
 ])
 assert INFO_DTYPE.itemsize == C.sizeof(Info)
@@ -67,6 +69,10 @@ class Options(C.Structure):
         ("max_iter", C.c_int32), ("check_every", C.c_int32), ("ruiz_iters", C.c_int32), ("cg_max", C.c_int32),
         ("eig_iters", C.c_int32), ("polish_outer", C.c_int32), ("polish_cg_max", C.c_int32),
         ("warm_start", C.c_int32), ("team", C.c_int32), ("threads", C.c_int32),
+        ("method", C.c_int32), ("ipm_max_iter", C.c_int32), ("fallback_max_iter", C.c_int32),
+        ("ipm_eps", C.c_double), ("ipm_delta0", C.c_double), ("ipm_delta_min", C.c_double), ("ipm_rho0", C.c_double),
+        ("ipm_tau", C.c_double), ("ipm_mu0", C.c_double), ("ipm_mu_min", C.c_double), ("ipm_kappa_eps", C.c_double),
+        ("ipm_refine", C.c_int32), ("verbose", C.c_int32), ("smem_kb", C.c_int32),
     ]
 
 
@@ -74,7 +80,8 @@ EXPORTS = [
     "sqpqp_create", "sqpqp_destroy", "sqpqp_last_error", "sqpqp_default_options", "sqpqp_set_options", "sqpqp_stream",
     "sqpqp_setup_nlp", "sqpqp_update_nlp", "sqpqp_update_nlp_device", "sqpqp_solve_tr", "sqpqp_num_slacks",
     "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
-    "sqpqp_launch_count", "sqpqp_last_solve_ms",
+    "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
+    "sqpqp_fetch_info", "sqpqp_chol_stats",
 ]
 
 
@@ -123,6 +130,11 @@ def lib():
     L.sqpqp_update_nlp.argtypes = [vp, _dp, _dp, _dp, _dp]
     L.sqpqp_update_nlp_device.argtypes = [vp, vp, vp, vp, vp]
     L.sqpqp_solve_tr.argtypes = [vp, C.c_int32, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _ip, C.c_void_p]
+    L.sqpqp_solve_tr_device.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
+    L.sqpqp_sync.argtypes = [vp]
+    L.sqpqp_device_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.sqpqp_fetch_info.argtypes = [vp, C.c_void_p]
+    L.sqpqp_chol_stats.argtypes = [vp, _lp, _lp, _lp]
     L.sqpqp_num_slacks.argtypes = [vp, _ip]
     L.sqpqp_merit.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp]
     L.sqpqp_kt_residuals.argtypes = [vp, _dp, _dp, _dp, _dp]
@@ -250,6 +262,27 @@ class Engine:
         self._ck(self.L.sqpqp_solve_tr(self.h, phase, _d(x_k), _d(delta), _d(E_override), _i(act), _d(p), _d(lam), _d(mxL),
                                        _d(mxU), _d(slack), _i(status), info.ctypes.data_as(C.c_void_p)))
         return p, lam, mxL, mxU, slack[:, :S], status, info
+
+    def solve_tr_device(self, phase, x_k_ptr, delta_ptr, E_override_ptr=None, active_ptr=None):
+        """Device-pointer, non-blocking variant (ints are raw device addresses)."""
+        self._ck(self.L.sqpqp_solve_tr_device(self.h, phase, x_k_ptr, delta_ptr, E_override_ptr, active_ptr))
+
+    def sync(self):
+        self._ck(self.L.sqpqp_sync(self.h))
+
+    def fetch_info(self):
+        info = np.zeros(self.batch, dtype=INFO_DTYPE)
+        self._ck(self.L.sqpqp_fetch_info(self.h, info.ctypes.data_as(C.c_void_p)))
+        return info
+
+    def chol_stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.L.sqpqp_chol_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"nnzL": a.value, "levels": b.value, "flops": c.value}
+
+    @property
+    def stream(self):
+        return int(self.L.sqpqp_stream(self.h) or 0)
 
     def merit(self, x, p, E_trial, f_trial, mu, fr=None):
         B, n, m = self.batch, self.n, self.m

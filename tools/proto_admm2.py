@@ -45,6 +45,7 @@ class Opts:
     feas_tol = 1e-9
     dual_tol = 1e-9
     verbose = False
+    polish_direct = False
     cg_rel0 = 0.1
     exact_reduced = False
     rb_mult = 2.0
@@ -216,9 +217,22 @@ def polish(Ps, qs, Js, JsT, rls, rus, xls, xus, x, act, yc, dP, J2T, o):
     Minv = 1.0 / np.maximum(dP + sig + rhoP * (J2T @ w), 1e-12)
     tot = 0
     r = np.zeros_like(w)
+    if o.polish_direct:
+        import scipy.sparse.linalg as spla
+        fi = np.nonzero(free)[0]
+        Kf = (Ps + sig * sp.identity(Ps.shape[0]) + rhoP * (JsT @ sp.diags(w) @ Js)).tocsc()
+        Kff = Kf[fi][:, fi].tocsc()
+        lu = spla.splu(Kff)
     for it in range(o.polish_outer):
         rhs = sig * xp - qs + JsT @ (w * (rhoP * bc - y))
-        xt, cg, rn, neg = pcg(Kmul, Minv, rhs, xp, max(1e-13 * np.sqrt(rhs @ rhs), 1e-300), 3000, mask=mask)
+        if o.polish_direct:
+            xc = np.where(free, 0.0, xfix)
+            rf = (rhs - Kf @ xc)[fi]
+            xf = lu.solve(rf)
+            xf += lu.solve(rf - Kff @ xf)
+            xt = xc.copy(); xt[fi] = xf; cg = 1; neg = False
+        else:
+            xt, cg, rn, neg = pcg(Kmul, Minv, rhs, xp, max(1e-13 * np.sqrt(rhs @ rhs), 1e-300), 3000, mask=mask)
         tot += cg
         if neg:
             return None
