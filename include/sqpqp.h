@@ -94,6 +94,7 @@ typedef struct sqpqp_options {
     double ipm_eps, ipm_delta0, ipm_delta_min, ipm_rho0, ipm_tau, ipm_mu0, ipm_mu_min, ipm_kappa_eps;
     int32_t ipm_refine;      /* iterative-refinement steps per Newton solve */
     int32_t verbose;         /* 1: device printf of the interior-point iterations (debugging) */
+    int32_t occupancy;       /* CTA kernel variant: 0 auto, 1 = 128 regs/thread, 4 or 8 = 64 regs (min CTAs per SM) */
     int32_t smem_kb;         /* shared-memory budget per CTA for resident scratch arrays; -1 = auto, 0 = none */
 } sqpqp_options;
 

@@ -72,7 +72,7 @@ class Options(C.Structure):
         ("method", C.c_int32), ("ipm_max_iter", C.c_int32), ("fallback_max_iter", C.c_int32),
         ("ipm_eps", C.c_double), ("ipm_delta0", C.c_double), ("ipm_delta_min", C.c_double), ("ipm_rho0", C.c_double),
         ("ipm_tau", C.c_double), ("ipm_mu0", C.c_double), ("ipm_mu_min", C.c_double), ("ipm_kappa_eps", C.c_double),
-        ("ipm_refine", C.c_int32), ("verbose", C.c_int32), ("smem_kb", C.c_int32),
+        ("ipm_refine", C.c_int32), ("verbose", C.c_int32), ("occupancy", C.c_int32), ("smem_kb", C.c_int32),
     ]
 
 

@@ -740,7 +740,11 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
 }
 
 // ---- kernels ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) k_solve_cta(Prob P, DevOpts O, int phase, Placement pl) {
+// MAXT threads per CTA, at least MINB CTAs per SM: <512,1> keeps 128 registers/thread for the
+// one-CTA-per-SM resident configuration; <256,4> and <128,8> cap registers at 64 so that many
+// instances share an SM and hide each other's (L2-latency-bound) level-scheduled phases.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(Prob P, DevOpts O, int phase, Placement pl) {
     __shared__ double sh[2 * SQPQP_MAX_RED * 32];
     extern __shared__ double dsm[];
     for (int inst = blockIdx.x; inst < P.batch; inst += gridDim.x) {

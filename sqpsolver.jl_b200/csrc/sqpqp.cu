@@ -215,9 +215,9 @@ extern "C" void sqpqp_default_options(sqpqp_options* o) {
     o->polish_trigger = 5e-2; o->polish_rho = 1e4; o->polish_tol = 1e-11; o->feas_tol = 1e-9; o->dual_tol = 1e-9;
     o->max_iter = 6000; o->check_every = 25; o->ruiz_iters = 15; o->cg_max = 300; o->eig_iters = 60;
     o->polish_outer = 20; o->polish_cg_max = 3000;
-    o->warm_start = 1; o->team = 0; o->threads = 0; o->smem_kb = -1;
+    o->warm_start = 1; o->team = 0; o->threads = 0; o->smem_kb = -1; o->occupancy = 0;
     o->method = 0; o->ipm_max_iter = 200; o->fallback_max_iter = 1500; o->ipm_eps = 1e-9; o->ipm_delta0 = 1e-6; o->ipm_delta_min = 1e-8;
-    o->ipm_rho0 = 1e-8; o->ipm_tau = 0.995; o->ipm_mu0 = 1.0; o->ipm_mu_min = 1e-14; o->ipm_kappa_eps = 10.0; o->ipm_refine = 1; o->verbose = 0;
+    o->ipm_rho0 = 1e-8; o->ipm_tau = 0.995; o->ipm_mu0 = 1.0; o->ipm_mu_min = 1e-14; o->ipm_kappa_eps = 10.0; o->ipm_refine = 0; o->verbose = 0;
 }
 
 extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
@@ -241,7 +241,9 @@ extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     h->max_dyn_smem = optin - 4096 - 1024;  // static reduction scratch + slack
     if (h->max_dyn_smem < 0) h->max_dyn_smem = 0;
-    cudaFuncSetAttribute(k_solve_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
+    cudaFuncSetAttribute(k_solve_cta<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
+    cudaFuncSetAttribute(k_solve_cta<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+    cudaFuncSetAttribute(k_solve_cta<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024);
     *out = h;
     return 0;
 }
@@ -634,7 +636,11 @@ static int launch_solve(sqpqp_handle h, int phase) {
         bool ipm = (phase == SQPQP_PHASE_FR ? P.has_chol_fr : P.has_chol) && h->opts.method != 1;
         place_arrays(P, phase, budget, ipm, &pl);
         size_t dyn = (size_t)pl.total * sizeof(double);
-        k_solve_cta<<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+        int occ = h->opts.occupancy;  // 0 auto
+        if (occ == 0) occ = many ? 4 : 1;
+        if (occ >= 8 && threads <= 128) k_solve_cta<128, 8><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+        else if (occ >= 4 && threads <= 256) k_solve_cta<256, 4><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+        else k_solve_cta<512, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
     }
     h->launches++;
     CUDA_OK(cudaEventRecord(h->ev1, h->stream));
