@@ -37,49 +37,41 @@ template <class Team>
 __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval, double* yw, const sqpqp_options& o,
                           double c, int phase, const double* xk_scaled_start) {
     const int N = I.N, M = I.M;
-    // scaled problem data (set up by solve_instance)
-    const double *q = I.nv[N_Q], *xl = I.nv[N_XL], *xu = I.nv[N_XU], *D = I.nv[N_D], *hd = I.nv[N_HD];
-    const double *rl = I.mv[M_RL], *ru = I.mv[M_RU], *Es = I.mv[M_ES];
-    // IPM state (aliases of the ADMM workspace slots; the two methods never run concurrently)
-    double *x = I.nv[N_X], *dx = I.nv[N_XT], *rx = I.nv[N_R], *rhs = I.nv[N_P];
-    double *sxu = I.nv[N_ZB], *zxu = I.nv[N_YB], *sxl = I.nv[N_RB], *zxl = I.nv[N_KP];
-    double *cxu = I.nv[N_MINV], *cxl = I.nv[N_XFIX], *yx = I.nv[N_MASK], *wb = I.nv[N_DSH], *tmpN = I.nv[N_TMP];
-    double *sru = I.mv[M_ZC], *zru = I.mv[M_YC], *srl = I.mv[M_RC], *zrl = I.mv[M_BC];
-    double *cru = I.mv[M_YP], *crl = I.mv[M_TMP], *y = I.mv[M_I1], *w = I.mv[M_RW], *t = I.mv[M_T];
-    double *jdx = I.mv[M_I2], *Ax = I.mv[M_I3];
-    // side residuals are TRACKED (r += alpha (g dx + ds)), never recomputed from A x - b: at the end
-    // of the solve delta ~ 1e-11 and a freshly evaluated residual carries ~1e-16 |Ax| of rounding
-    // noise, which the dual update dy = (J dx + r)/delta would amplify by 1e11
-    double *rru = I.mv[M_AX], *rrl = I.mv[M_I4], *rxu = I.nv[N_TMP2], *rxl = I.nv[N_I1];
-
+    // Work vectors are addressed through the (shared-memory resident) pointer table of `I` at every use
+    // instead of through ~36 local pointer aliases: 72 fewer live registers, which is what lets the
+    // 64-register / 4-CTAs-per-SM variant of the kernel run without spilling its address arithmetic.
+    // Aliases of the ADMM workspace slots (the two methods never run concurrently); side residuals are
+    // TRACKED (r += alpha (g dx + ds)), never recomputed from A x - b: at the end of the solve
+    // delta ~ 1e-8 and a freshly evaluated residual carries ~1e-16 |Ax| of rounding noise, which the
+    // dual update dy = (J dx + r)/delta would amplify by 1/delta.
     IpmOut out{false, false, false, false, 0, 0, INFINITY, INFINITY, 0.0};
-    // ---- start point: x inside the box, unit duals, slacks >= 1 --------------------------------
+    // ---- start point: I.nv[N_X] inside the box, unit duals, slacks >= 1 --------------------------------
     for_n(T, N, [&](int j) {
         double v = xk_scaled_start ? xk_scaled_start[j] : 0.0;
-        v = fmin(fmax(v, xl[j]), xu[j]);
-        x[j] = v;
-        yx[j] = 0.0;
+        v = fmin(fmax(v, I.nv[N_XL][j]), I.nv[N_XU][j]);
+        I.nv[N_X][j] = v;
+        I.nv[N_MASK][j] = 0.0;
     });
     T.sync();
     double cnt[1] = {0.0};
-    csr_rows(T, M, I.lgJ, I.J.rb, I.J.re, I.J.col, I.Jsv, x, [&](int i, double ax) {
-        bool eq = rl[i] == ru[i];
-        bool uf = !eq && !isinf(ru[i]), lf = !eq && !isinf(rl[i]);
-        sru[i] = uf ? fmax(ru[i] - ax, 1.0) : 1.0; zru[i] = uf ? 1.0 : 0.0;
-        srl[i] = lf ? fmax(ax - rl[i], 1.0) : 1.0; zrl[i] = lf ? 1.0 : 0.0;
-        y[i] = 0.0;
-        Ax[i] = ax;
-        rru[i] = eq ? ax - rl[i] : (uf ? ax + sru[i] - ru[i] : 0.0);
-        rrl[i] = lf ? -ax + srl[i] + rl[i] : 0.0;
+    csr_rows(T, M, I.lgJ, I.J.rb, I.J.re, I.J.col, I.Jsv, I.nv[N_X], [&](int i, double ax) {
+        bool eq = I.mv[M_RL][i] == I.mv[M_RU][i];
+        bool uf = !eq && !isinf(I.mv[M_RU][i]), lf = !eq && !isinf(I.mv[M_RL][i]);
+        I.mv[M_ZC][i] = uf ? fmax(I.mv[M_RU][i] - ax, 1.0) : 1.0; I.mv[M_YC][i] = uf ? 1.0 : 0.0;
+        I.mv[M_RC][i] = lf ? fmax(ax - I.mv[M_RL][i], 1.0) : 1.0; I.mv[M_BC][i] = lf ? 1.0 : 0.0;
+        I.mv[M_I1][i] = 0.0;
+        I.mv[M_I3][i] = ax;
+        I.mv[M_AX][i] = eq ? ax - I.mv[M_RL][i] : (uf ? ax + I.mv[M_ZC][i] - I.mv[M_RU][i] : 0.0);
+        I.mv[M_I4][i] = lf ? -ax + I.mv[M_RC][i] + I.mv[M_RL][i] : 0.0;
         cnt[0] += (double)uf + (double)lf;
     });
     for_n(T, N, [&](int j) {
-        bool eq = xl[j] == xu[j];
-        bool uf = !eq && !isinf(xu[j]), lf = !eq && !isinf(xl[j]);
-        sxu[j] = uf ? fmax(xu[j] - x[j], 1.0) : 1.0; zxu[j] = uf ? 1.0 : 0.0;
-        sxl[j] = lf ? fmax(x[j] - xl[j], 1.0) : 1.0; zxl[j] = lf ? 1.0 : 0.0;
-        rxu[j] = eq ? x[j] - xl[j] : (uf ? x[j] + sxu[j] - xu[j] : 0.0);
-        rxl[j] = lf ? -x[j] + sxl[j] + xl[j] : 0.0;
+        bool eq = I.nv[N_XL][j] == I.nv[N_XU][j];
+        bool uf = !eq && !isinf(I.nv[N_XU][j]), lf = !eq && !isinf(I.nv[N_XL][j]);
+        I.nv[N_ZB][j] = uf ? fmax(I.nv[N_XU][j] - I.nv[N_X][j], 1.0) : 1.0; I.nv[N_YB][j] = uf ? 1.0 : 0.0;
+        I.nv[N_RB][j] = lf ? fmax(I.nv[N_X][j] - I.nv[N_XL][j], 1.0) : 1.0; I.nv[N_KP][j] = lf ? 1.0 : 0.0;
+        I.nv[N_TMP2][j] = eq ? I.nv[N_X][j] - I.nv[N_XL][j] : (uf ? I.nv[N_X][j] + I.nv[N_ZB][j] - I.nv[N_XU][j] : 0.0);
+        I.nv[N_I1][j] = lf ? -I.nv[N_X][j] + I.nv[N_RB][j] + I.nv[N_XL][j] : 0.0;
         cnt[0] += (double)uf + (double)lf;
     });
     T.template reduce<1, false>(cnt);
@@ -94,54 +86,54 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
         // ---- residuals ----------------------------------------------------------------------
         T.sync();
         double ymx[1] = {0.0};
-        for_n(T, M, [&](int i) { double v = (rl[i] == ru[i]) ? y[i] : (zru[i] - zrl[i]); t[i] = v; ymx[0] = fmax(ymx[0], fabs(v)); });
+        for_n(T, M, [&](int i) { double v = (I.mv[M_RL][i] == I.mv[M_RU][i]) ? I.mv[M_I1][i] : (I.mv[M_YC][i] - I.mv[M_BC][i]); I.mv[M_T][i] = v; ymx[0] = fmax(ymx[0], fabs(v)); });
         T.template reduce<1, true>(ymx);
         if (ymx[0] > 1e12) { out.blowup = true; break; }  // multipliers exploding: ADMM certifies infeasibility
         double mx[6] = {0, 0, 0, 0, 0, 0};  // [0] rp [1] rd*c [2] primal scale [3] dual scale*c [4] |A'lam|*c [5] |lam|*c (unscaled)
         double sup[1] = {0.0};  // support function  u'(lam)+ + l'(lam)-  (scaled units = unscaled * c)
         double sm[1] = {0.0};         // sum s*z
         double sz[3] = {0.0, -INFINITY, 0.0};  // [0] max s*z  [1] max -(s*z) = -min s*z  [2] scaled residual of the barrier problem
-        csr_rows2(T, N, I.lgT, I.H.rb, I.H.re, I.H.col, I.Hsv, x, I.useH, I.T.rb, I.T.re, I.T.col, I.Tsv, t,
+        csr_rows2(T, N, I.lgT, I.H.rb, I.H.re, I.H.col, I.Hsv, I.nv[N_X], I.useH, I.T.rb, I.T.re, I.T.col, I.Tsv, I.mv[M_T],
                   [&](int j, double px, double aty) {
-                      if (!I.useH) px = hd[j] * x[j];
-                      bool eq = xl[j] == xu[j];
-                      double lamb = eq ? yx[j] : (zxu[j] - zxl[j]);
-                      double r = px + q[j] + aty + lamb;
-                      rx[j] = r;
-                      mx[4] = fmax(mx[4], fabs(aty + lamb) / D[j]);
-                      mx[5] = fmax(mx[5], fabs(lamb) / D[j]);
-                      if (lamb > 0.0) sup[0] += xu[j] * lamb; else if (lamb < 0.0) sup[0] += xl[j] * lamb;
+                      if (!I.useH) px = I.nv[N_HD][j] * I.nv[N_X][j];
+                      bool eq = I.nv[N_XL][j] == I.nv[N_XU][j];
+                      double lamb = eq ? I.nv[N_MASK][j] : (I.nv[N_YB][j] - I.nv[N_KP][j]);
+                      double r = px + I.nv[N_Q][j] + aty + lamb;
+                      I.nv[N_R][j] = r;
+                      mx[4] = fmax(mx[4], fabs(aty + lamb) / I.nv[N_D][j]);
+                      mx[5] = fmax(mx[5], fabs(lamb) / I.nv[N_D][j]);
+                      if (lamb > 0.0) sup[0] += I.nv[N_XU][j] * lamb; else if (lamb < 0.0) sup[0] += I.nv[N_XL][j] * lamb;
                       sz[2] = fmax(sz[2], fabs(r));
-                      double id = 1.0 / D[j];
+                      double id = 1.0 / I.nv[N_D][j];
                       mx[1] = fmax(mx[1], fabs(r) * id);
                       if (o.verbose > 1 && it >= 9 && fabs(r) * id / c > 1e-4)
-                          printf("      j=%d r=%.3e px=%.3e q=%.3e aty=%.3e lamb=%.3e x=%.6e xl=%.6e xu=%.6e sxu=%.3e zxu=%.3e sxl=%.3e zxl=%.3e D=%.2e\n",
-                                 j, r, px, q[j], aty, lamb, x[j], xl[j], xu[j], sxu[j], zxu[j], sxl[j], zxl[j], D[j]);
-                      mx[3] = fmax(mx[3], fmax(fabs(px), fmax(fabs(aty), fabs(q[j]))) * id);
-                      mx[2] = fmax(mx[2], fabs(x[j]) * D[j]);
+                          printf("      j=%d r=%.3e px=%.3e I.nv[N_Q]=%.3e aty=%.3e lamb=%.3e I.nv[N_X]=%.6e I.nv[N_XL]=%.6e I.nv[N_XU]=%.6e I.nv[N_ZB]=%.3e I.nv[N_YB]=%.3e I.nv[N_RB]=%.3e I.nv[N_KP]=%.3e I.nv[N_D]=%.2e\n",
+                                 j, r, px, I.nv[N_Q][j], aty, lamb, I.nv[N_X][j], I.nv[N_XL][j], I.nv[N_XU][j], I.nv[N_ZB][j], I.nv[N_YB][j], I.nv[N_RB][j], I.nv[N_KP][j], I.nv[N_D][j]);
+                      mx[3] = fmax(mx[3], fmax(fabs(px), fmax(fabs(aty), fabs(I.nv[N_Q][j]))) * id);
+                      mx[2] = fmax(mx[2], fabs(I.nv[N_X][j]) * I.nv[N_D][j]);
                       double pr = 0.0;
-                      if (eq) pr = fabs(rxu[j]);
+                      if (eq) pr = fabs(I.nv[N_TMP2][j]);
                       else {
-                          if (!isinf(xu[j])) { double p_ = sxu[j] * zxu[j]; pr = fmax(pr, fabs(rxu[j])); sm[0] += p_; sz[0] = fmax(sz[0], p_); sz[1] = fmax(sz[1], -p_); }
-                          if (!isinf(xl[j])) { double p_ = sxl[j] * zxl[j]; pr = fmax(pr, fabs(rxl[j])); sm[0] += p_; sz[0] = fmax(sz[0], p_); sz[1] = fmax(sz[1], -p_); }
+                          if (!isinf(I.nv[N_XU][j])) { double p_ = I.nv[N_ZB][j] * I.nv[N_YB][j]; pr = fmax(pr, fabs(I.nv[N_TMP2][j])); sm[0] += p_; sz[0] = fmax(sz[0], p_); sz[1] = fmax(sz[1], -p_); }
+                          if (!isinf(I.nv[N_XL][j])) { double p_ = I.nv[N_RB][j] * I.nv[N_KP][j]; pr = fmax(pr, fabs(I.nv[N_I1][j])); sm[0] += p_; sz[0] = fmax(sz[0], p_); sz[1] = fmax(sz[1], -p_); }
                       }
                       sz[2] = fmax(sz[2], pr);
-                      mx[0] = fmax(mx[0], pr * D[j]);
+                      mx[0] = fmax(mx[0], pr * I.nv[N_D][j]);
                   });
         for_n(T, M, [&](int i) {
-            bool eq = rl[i] == ru[i];
-            double pr = 0.0, ax = Ax[i];
-            if (eq) pr = fabs(rru[i]);
+            bool eq = I.mv[M_RL][i] == I.mv[M_RU][i];
+            double pr = 0.0, ax = I.mv[M_I3][i];
+            if (eq) pr = fabs(I.mv[M_AX][i]);
             else {
-                if (!isinf(ru[i])) { double p_ = sru[i] * zru[i]; pr = fmax(pr, fabs(rru[i])); sm[0] += p_; sz[0] = fmax(sz[0], p_); sz[1] = fmax(sz[1], -p_); }
-                if (!isinf(rl[i])) { double p_ = srl[i] * zrl[i]; pr = fmax(pr, fabs(rrl[i])); sm[0] += p_; sz[0] = fmax(sz[0], p_); sz[1] = fmax(sz[1], -p_); }
+                if (!isinf(I.mv[M_RU][i])) { double p_ = I.mv[M_ZC][i] * I.mv[M_YC][i]; pr = fmax(pr, fabs(I.mv[M_AX][i])); sm[0] += p_; sz[0] = fmax(sz[0], p_); sz[1] = fmax(sz[1], -p_); }
+                if (!isinf(I.mv[M_RL][i])) { double p_ = I.mv[M_RC][i] * I.mv[M_BC][i]; pr = fmax(pr, fabs(I.mv[M_I4][i])); sm[0] += p_; sz[0] = fmax(sz[0], p_); sz[1] = fmax(sz[1], -p_); }
             }
             sz[2] = fmax(sz[2], pr);
-            mx[0] = fmax(mx[0], pr / Es[i]);
-            mx[2] = fmax(mx[2], fabs(ax) / Es[i]);
-            double lr = t[i];
-            mx[5] = fmax(mx[5], fabs(lr) * Es[i]);
-            if (lr > 0.0) sup[0] += ru[i] * lr; else if (lr < 0.0) sup[0] += rl[i] * lr;
+            mx[0] = fmax(mx[0], pr / I.mv[M_ES][i]);
+            mx[2] = fmax(mx[2], fabs(ax) / I.mv[M_ES][i]);
+            double lr = I.mv[M_T][i];
+            mx[5] = fmax(mx[5], fabs(lr) * I.mv[M_ES][i]);
+            if (lr > 0.0) sup[0] += I.mv[M_RU][i] * lr; else if (lr < 0.0) sup[0] += I.mv[M_RL][i] * lr;
         });
         T.template reduce<6, true>(mx);
         T.template reduce<1, false>(sup);
@@ -168,7 +160,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
             if (stalled) { out.infeasible = true; break; }
         }
         if (it % 10 == 0) rp_ref = out.rp;
-        // Termination (Ipopt-style scaling): primal residual relative to |x|,|Ax|; stationarity relative to
+        // Termination (Ipopt-style scaling): primal residual relative to |I.nv[N_X]|,|I.mv[M_I3]|; stationarity relative to
         // the gradient terms (its attainable floor is ~1e-9 of them, the conditioning of K); complementarity
         // (largest s*z, unscaled) absolute unless the multipliers themselves are large.
         const double comp_u = sz[0] / c, sc = fmax(1.0, ymx[0] / c / 100.0);
@@ -186,10 +178,10 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
         }
         if (o.verbose) {
             double ym[3] = {0, 0, 0};
-            for_n(T, M, [&](int i) { ym[0] = fmax(ym[0], fabs(y[i])); ym[1] = fmax(ym[1], fmax(zru[i], zrl[i])); });
-            for_n(T, N, [&](int j) { ym[1] = fmax(ym[1], fmax(zxu[j], zxl[j])); ym[2] = fmax(ym[2], fabs(x[j])); });
+            for_n(T, M, [&](int i) { ym[0] = fmax(ym[0], fabs(I.mv[M_I1][i])); ym[1] = fmax(ym[1], fmax(I.mv[M_YC][i], I.mv[M_BC][i])); });
+            for_n(T, N, [&](int j) { ym[1] = fmax(ym[1], fmax(I.nv[N_YB][j], I.nv[N_KP][j])); ym[2] = fmax(ym[2], fabs(I.nv[N_X][j])); });
             T.template reduce<3, true>(ym);
-            if (T.tid() == 0) printf("      |y|=%.2e |z|=%.2e |x|=%.2e c=%.2e\n", ym[0], ym[1], ym[2], c);
+            if (T.tid() == 0) printf("      |I.mv[M_I1]|=%.2e |z|=%.2e |I.nv[N_X]|=%.2e c=%.2e\n", ym[0], ym[1], ym[2], c);
         }
         if (o.verbose && T.tid() == 0)
             printf("  ipm %3d rp=%.2e rd=%.2e mu=%.2e delta=%.1e rho=%.1e nfact=%d\n", it, out.rp, out.rd, mu / c, delta, rho_p, out.nfact);
@@ -203,29 +195,29 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
         }
         // ---- weights, assembly, factorisation (with inertia correction) ---------------------------
         for_n(T, M, [&](int i) {
-            bool eq = rl[i] == ru[i];
+            bool eq = I.mv[M_RL][i] == I.mv[M_RU][i];
             double wi = 0.0;
             if (eq) wi = 1.0 / delta;
             else {
-                if (!isinf(ru[i])) wi += zru[i] / (sru[i] + delta * zru[i]);
-                if (!isinf(rl[i])) wi += zrl[i] / (srl[i] + delta * zrl[i]);
+                if (!isinf(I.mv[M_RU][i])) wi += I.mv[M_YC][i] / (I.mv[M_ZC][i] + delta * I.mv[M_YC][i]);
+                if (!isinf(I.mv[M_RL][i])) wi += I.mv[M_BC][i] / (I.mv[M_RC][i] + delta * I.mv[M_BC][i]);
             }
-            w[i] = wi;
+            I.mv[M_RW][i] = wi;
         });
         bool fact_ok = false;
         for (int tries = 0; tries < 30 && !fact_ok; ++tries) {
             for_n(T, N, [&](int j) {
-                bool eq = xl[j] == xu[j];
+                bool eq = I.nv[N_XL][j] == I.nv[N_XU][j];
                 double wj = 0.0;
                 if (eq) wj = 1.0 / delta;
                 else {
-                    if (!isinf(xu[j])) wj += zxu[j] / (sxu[j] + delta * zxu[j]);
-                    if (!isinf(xl[j])) wj += zxl[j] / (sxl[j] + delta * zxl[j]);
+                    if (!isinf(I.nv[N_XU][j])) wj += I.nv[N_YB][j] / (I.nv[N_ZB][j] + delta * I.nv[N_YB][j]);
+                    if (!isinf(I.nv[N_XL][j])) wj += I.nv[N_KP][j] / (I.nv[N_RB][j] + delta * I.nv[N_KP][j]);
                 }
-                wb[j] = wj + rho_p + (I.useH ? 0.0 : hd[j]);
+                I.nv[N_DSH][j] = wj + rho_p + (I.useH ? 0.0 : I.nv[N_HD][j]);
             });
             T.sync();
-            chol_assemble(T, C, Lval, I.useH ? I.Hsv : (const double*)nullptr, wb, w, I.Jsv);
+            chol_assemble(T, C, Lval, I.useH ? I.Hsv : (const double*)nullptr, I.nv[N_DSH], I.mv[M_RW], I.Jsv);
             fact_ok = chol_factor(T, C, Lval);
             ++out.nfact;
             if (!fact_ok) rho_p = fmax(fmax(10.0 * rho_p, rho_last > 0.0 ? rho_last / 3.0 : 1e-4), 1e-6);
@@ -239,92 +231,92 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
         double sigma_mu = mu_t, alpha = 1.0;
         const double tau_k = fmax(o.ipm_tau, 1.0 - mu_t);
         for (int pass = 1; pass < 2; ++pass) {
-            // t_row, then rhs = -r_x - T t_row - t_box
+            // t_row, then I.nv[N_P] = -r_x - T t_row - t_box
             for_n(T, M, [&](int i) {
-                bool eq = rl[i] == ru[i];
-                double ax = Ax[i], ti = 0.0;
-                if (eq) ti = rru[i] / delta;
+                bool eq = I.mv[M_RL][i] == I.mv[M_RU][i];
+                double ax = I.mv[M_I3][i], ti = 0.0;
+                if (eq) ti = I.mv[M_AX][i] / delta;
                 else {
-                    if (!isinf(ru[i])) {
-                        double rc = sigma_mu - sru[i] * zru[i] - 0.0;
-                        ti += (rc + zru[i] * (rru[i])) / (sru[i] + delta * zru[i]);
+                    if (!isinf(I.mv[M_RU][i])) {
+                        double rc = sigma_mu - I.mv[M_ZC][i] * I.mv[M_YC][i] - 0.0;
+                        ti += (rc + I.mv[M_YC][i] * (I.mv[M_AX][i])) / (I.mv[M_ZC][i] + delta * I.mv[M_YC][i]);
                     }
-                    if (!isinf(rl[i])) {
-                        double rc = sigma_mu - srl[i] * zrl[i] - 0.0;
-                        ti -= (rc + zrl[i] * (rrl[i])) / (srl[i] + delta * zrl[i]);
+                    if (!isinf(I.mv[M_RL][i])) {
+                        double rc = sigma_mu - I.mv[M_RC][i] * I.mv[M_BC][i] - 0.0;
+                        ti -= (rc + I.mv[M_BC][i] * (I.mv[M_I4][i])) / (I.mv[M_RC][i] + delta * I.mv[M_BC][i]);
                     }
                 }
-                t[i] = ti;
+                I.mv[M_T][i] = ti;
             });
             T.sync();
-            csr_rows(T, N, I.lgT, I.T.rb, I.T.re, I.T.col, I.Tsv, t, [&](int j, double tt) {
-                bool eq = xl[j] == xu[j];
+            csr_rows(T, N, I.lgT, I.T.rb, I.T.re, I.T.col, I.Tsv, I.mv[M_T], [&](int j, double tt) {
+                bool eq = I.nv[N_XL][j] == I.nv[N_XU][j];
                 double tb = 0.0;
-                if (eq) tb = rxu[j] / delta;
+                if (eq) tb = I.nv[N_TMP2][j] / delta;
                 else {
-                    if (!isinf(xu[j])) {
-                        double rc = sigma_mu - sxu[j] * zxu[j] - 0.0;
-                        tb += (rc + zxu[j] * (rxu[j])) / (sxu[j] + delta * zxu[j]);
+                    if (!isinf(I.nv[N_XU][j])) {
+                        double rc = sigma_mu - I.nv[N_ZB][j] * I.nv[N_YB][j] - 0.0;
+                        tb += (rc + I.nv[N_YB][j] * (I.nv[N_TMP2][j])) / (I.nv[N_ZB][j] + delta * I.nv[N_YB][j]);
                     }
-                    if (!isinf(xl[j])) {
-                        double rc = sigma_mu - sxl[j] * zxl[j] - 0.0;
-                        tb -= (rc + zxl[j] * (rxl[j])) / (sxl[j] + delta * zxl[j]);
+                    if (!isinf(I.nv[N_XL][j])) {
+                        double rc = sigma_mu - I.nv[N_RB][j] * I.nv[N_KP][j] - 0.0;
+                        tb -= (rc + I.nv[N_KP][j] * (I.nv[N_I1][j])) / (I.nv[N_RB][j] + delta * I.nv[N_KP][j]);
                     }
                 }
-                rhs[j] = -rx[j] - tt - tb;
+                I.nv[N_P][j] = -I.nv[N_R][j] - tt - tb;
             });
             T.sync();
-            chol_solve(T, C, Lval, rhs, dx, yw);
+            chol_solve(T, C, Lval, I.nv[N_P], I.nv[N_XT], yw);
             // iterative refinement against the matrix-free K (K is ill-conditioned by design)
             for (int rf = 0; rf < o.ipm_refine; ++rf) {
-                apply_K(T, I, dx, tmpN, wb, w, (const double*)nullptr);
+                apply_K(T, I, I.nv[N_XT], I.nv[N_TMP], I.nv[N_DSH], I.mv[M_RW], (const double*)nullptr);
                 T.sync();
-                // apply_K adds hd for !useH on top of dsh; wb already contains it -> subtract once
+                // apply_K adds I.nv[N_HD] for !useH on top of dsh; I.nv[N_DSH] already contains it -> subtract once
                 double nr[2] = {0.0, 0.0};
                 for_n(T, N, [&](int j) {
-                    double kv = tmpN[j] - (I.useH ? 0.0 : hd[j] * dx[j]);
-                    double r = rhs[j] - kv;
-                    tmpN[j] = r;
+                    double kv = I.nv[N_TMP][j] - (I.useH ? 0.0 : I.nv[N_HD][j] * I.nv[N_XT][j]);
+                    double r = I.nv[N_P][j] - kv;
+                    I.nv[N_TMP][j] = r;
                     nr[0] = fmax(nr[0], fabs(r));
-                    nr[1] = fmax(nr[1], fabs(rhs[j]));
+                    nr[1] = fmax(nr[1], fabs(I.nv[N_P][j]));
                 });
                 if (o.verbose) {
                     T.template reduce<2, true>(nr);
-                    if (T.tid() == 0) printf("      pass %d refine %d: |rhs - K dx| = %.2e  |rhs| = %.2e\n", pass, rf, nr[0], nr[1]);
+                    if (T.tid() == 0) printf("      pass %d refine %d: |I.nv[N_P] - K I.nv[N_XT]| = %.2e  |I.nv[N_P]| = %.2e\n", pass, rf, nr[0], nr[1]);
                 }
                 T.sync();
-                chol_solve(T, C, Lval, tmpN, tmpN, yw);
-                for_n(T, N, [&](int j) { dx[j] += tmpN[j]; });
+                chol_solve(T, C, Lval, I.nv[N_TMP], I.nv[N_TMP], yw);
+                for_n(T, N, [&](int j) { I.nv[N_XT][j] += I.nv[N_TMP][j]; });
                 T.sync();
             }
-            // J dx and the step-to-boundary ratio
+            // J I.nv[N_XT] and the step-to-boundary ratio
             double ratio[1] = {0.0};
-            csr_rows(T, M, I.lgJ, I.J.rb, I.J.re, I.J.col, I.Jsv, dx, [&](int i, double jd) {
-                jdx[i] = jd;
-                if (rl[i] == ru[i]) return;
-                double ax = Ax[i];
-                if (!isinf(ru[i])) {
-                    double rc = sigma_mu - sru[i] * zru[i] - 0.0;
-                    SideDir d = side_dir(rc, zru[i], sru[i], rru[i], jd, delta);
-                    ratio[0] = fmax(ratio[0], fmax(step_ratio(sru[i], d.ds), step_ratio(zru[i], d.dz)));
+            csr_rows(T, M, I.lgJ, I.J.rb, I.J.re, I.J.col, I.Jsv, I.nv[N_XT], [&](int i, double jd) {
+                I.mv[M_I2][i] = jd;
+                if (I.mv[M_RL][i] == I.mv[M_RU][i]) return;
+                double ax = I.mv[M_I3][i];
+                if (!isinf(I.mv[M_RU][i])) {
+                    double rc = sigma_mu - I.mv[M_ZC][i] * I.mv[M_YC][i] - 0.0;
+                    SideDir d = side_dir(rc, I.mv[M_YC][i], I.mv[M_ZC][i], I.mv[M_AX][i], jd, delta);
+                    ratio[0] = fmax(ratio[0], fmax(step_ratio(I.mv[M_ZC][i], d.ds), step_ratio(I.mv[M_YC][i], d.dz)));
                 }
-                if (!isinf(rl[i])) {
-                    double rc = sigma_mu - srl[i] * zrl[i] - 0.0;
-                    SideDir d = side_dir(rc, zrl[i], srl[i], rrl[i], -jd, delta);
-                    ratio[0] = fmax(ratio[0], fmax(step_ratio(srl[i], d.ds), step_ratio(zrl[i], d.dz)));
+                if (!isinf(I.mv[M_RL][i])) {
+                    double rc = sigma_mu - I.mv[M_RC][i] * I.mv[M_BC][i] - 0.0;
+                    SideDir d = side_dir(rc, I.mv[M_BC][i], I.mv[M_RC][i], I.mv[M_I4][i], -jd, delta);
+                    ratio[0] = fmax(ratio[0], fmax(step_ratio(I.mv[M_RC][i], d.ds), step_ratio(I.mv[M_BC][i], d.dz)));
                 }
             });
             for_n(T, N, [&](int j) {
-                if (xl[j] == xu[j]) return;
-                if (!isinf(xu[j])) {
-                    double rc = sigma_mu - sxu[j] * zxu[j] - 0.0;
-                    SideDir d = side_dir(rc, zxu[j], sxu[j], rxu[j], dx[j], delta);
-                    ratio[0] = fmax(ratio[0], fmax(step_ratio(sxu[j], d.ds), step_ratio(zxu[j], d.dz)));
+                if (I.nv[N_XL][j] == I.nv[N_XU][j]) return;
+                if (!isinf(I.nv[N_XU][j])) {
+                    double rc = sigma_mu - I.nv[N_ZB][j] * I.nv[N_YB][j] - 0.0;
+                    SideDir d = side_dir(rc, I.nv[N_YB][j], I.nv[N_ZB][j], I.nv[N_TMP2][j], I.nv[N_XT][j], delta);
+                    ratio[0] = fmax(ratio[0], fmax(step_ratio(I.nv[N_ZB][j], d.ds), step_ratio(I.nv[N_YB][j], d.dz)));
                 }
-                if (!isinf(xl[j])) {
-                    double rc = sigma_mu - sxl[j] * zxl[j] - 0.0;
-                    SideDir d = side_dir(rc, zxl[j], sxl[j], rxl[j], -dx[j], delta);
-                    ratio[0] = fmax(ratio[0], fmax(step_ratio(sxl[j], d.ds), step_ratio(zxl[j], d.dz)));
+                if (!isinf(I.nv[N_XL][j])) {
+                    double rc = sigma_mu - I.nv[N_RB][j] * I.nv[N_KP][j] - 0.0;
+                    SideDir d = side_dir(rc, I.nv[N_KP][j], I.nv[N_RB][j], I.nv[N_I1][j], -I.nv[N_XT][j], delta);
+                    ratio[0] = fmax(ratio[0], fmax(step_ratio(I.nv[N_RB][j], d.ds), step_ratio(I.nv[N_KP][j], d.dz)));
                 }
             });
             T.template reduce<1, true>(ratio);
@@ -333,30 +325,30 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
                 // mu_aff and the second-order cross terms ds_aff * dz_aff
                 double ms[1] = {0.0};
                 for_n(T, M, [&](int i) {
-                    if (rl[i] == ru[i]) return;
-                    double ax = Ax[i], jd = jdx[i];
-                    if (!isinf(ru[i])) {
-                        SideDir d = side_dir(-sru[i] * zru[i], zru[i], sru[i], rru[i], jd, delta);
-                        cru[i] = d.ds * d.dz;
-                        ms[0] += (sru[i] + a_aff * d.ds) * (zru[i] + a_aff * d.dz);
+                    if (I.mv[M_RL][i] == I.mv[M_RU][i]) return;
+                    double ax = I.mv[M_I3][i], jd = I.mv[M_I2][i];
+                    if (!isinf(I.mv[M_RU][i])) {
+                        SideDir d = side_dir(-I.mv[M_ZC][i] * I.mv[M_YC][i], I.mv[M_YC][i], I.mv[M_ZC][i], I.mv[M_AX][i], jd, delta);
+                        I.mv[M_YP][i] = d.ds * d.dz;
+                        ms[0] += (I.mv[M_ZC][i] + a_aff * d.ds) * (I.mv[M_YC][i] + a_aff * d.dz);
                     }
-                    if (!isinf(rl[i])) {
-                        SideDir d = side_dir(-srl[i] * zrl[i], zrl[i], srl[i], rrl[i], -jd, delta);
-                        crl[i] = d.ds * d.dz;
-                        ms[0] += (srl[i] + a_aff * d.ds) * (zrl[i] + a_aff * d.dz);
+                    if (!isinf(I.mv[M_RL][i])) {
+                        SideDir d = side_dir(-I.mv[M_RC][i] * I.mv[M_BC][i], I.mv[M_BC][i], I.mv[M_RC][i], I.mv[M_I4][i], -jd, delta);
+                        I.mv[M_TMP][i] = d.ds * d.dz;
+                        ms[0] += (I.mv[M_RC][i] + a_aff * d.ds) * (I.mv[M_BC][i] + a_aff * d.dz);
                     }
                 });
                 for_n(T, N, [&](int j) {
-                    if (xl[j] == xu[j]) return;
-                    if (!isinf(xu[j])) {
-                        SideDir d = side_dir(-sxu[j] * zxu[j], zxu[j], sxu[j], rxu[j], dx[j], delta);
-                        cxu[j] = d.ds * d.dz;
-                        ms[0] += (sxu[j] + a_aff * d.ds) * (zxu[j] + a_aff * d.dz);
+                    if (I.nv[N_XL][j] == I.nv[N_XU][j]) return;
+                    if (!isinf(I.nv[N_XU][j])) {
+                        SideDir d = side_dir(-I.nv[N_ZB][j] * I.nv[N_YB][j], I.nv[N_YB][j], I.nv[N_ZB][j], I.nv[N_TMP2][j], I.nv[N_XT][j], delta);
+                        I.nv[N_MINV][j] = d.ds * d.dz;
+                        ms[0] += (I.nv[N_ZB][j] + a_aff * d.ds) * (I.nv[N_YB][j] + a_aff * d.dz);
                     }
-                    if (!isinf(xl[j])) {
-                        SideDir d = side_dir(-sxl[j] * zxl[j], zxl[j], sxl[j], rxl[j], -dx[j], delta);
-                        cxl[j] = d.ds * d.dz;
-                        ms[0] += (sxl[j] + a_aff * d.ds) * (zxl[j] + a_aff * d.dz);
+                    if (!isinf(I.nv[N_XL][j])) {
+                        SideDir d = side_dir(-I.nv[N_RB][j] * I.nv[N_KP][j], I.nv[N_KP][j], I.nv[N_RB][j], I.nv[N_I1][j], -I.nv[N_XT][j], delta);
+                        I.nv[N_XFIX][j] = d.ds * d.dz;
+                        ms[0] += (I.nv[N_RB][j] + a_aff * d.ds) * (I.nv[N_KP][j] + a_aff * d.dz);
                     }
                 });
                 T.template reduce<1, false>(ms);
@@ -372,30 +364,30 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
         }
         // ---- update with the corrector direction -------------------------------------------------------
         for_n(T, M, [&](int i) {
-            double ax = Ax[i], jd = jdx[i];
-            Ax[i] = ax + alpha * jd;
-            if (rl[i] == ru[i]) { y[i] += alpha * (jd + rru[i]) / delta; rru[i] += alpha * jd; return; }
-            if (!isinf(ru[i])) {
-                SideDir d = side_dir(sigma_mu - sru[i] * zru[i] , zru[i], sru[i], rru[i], jd, delta);
-                sru[i] += alpha * d.ds; zru[i] += alpha * d.dz; rru[i] += alpha * (jd + d.ds);
+            double ax = I.mv[M_I3][i], jd = I.mv[M_I2][i];
+            I.mv[M_I3][i] = ax + alpha * jd;
+            if (I.mv[M_RL][i] == I.mv[M_RU][i]) { I.mv[M_I1][i] += alpha * (jd + I.mv[M_AX][i]) / delta; I.mv[M_AX][i] += alpha * jd; return; }
+            if (!isinf(I.mv[M_RU][i])) {
+                SideDir d = side_dir(sigma_mu - I.mv[M_ZC][i] * I.mv[M_YC][i] , I.mv[M_YC][i], I.mv[M_ZC][i], I.mv[M_AX][i], jd, delta);
+                I.mv[M_ZC][i] += alpha * d.ds; I.mv[M_YC][i] += alpha * d.dz; I.mv[M_AX][i] += alpha * (jd + d.ds);
             }
-            if (!isinf(rl[i])) {
-                SideDir d = side_dir(sigma_mu - srl[i] * zrl[i] , zrl[i], srl[i], rrl[i], -jd, delta);
-                srl[i] += alpha * d.ds; zrl[i] += alpha * d.dz; rrl[i] += alpha * (-jd + d.ds);
+            if (!isinf(I.mv[M_RL][i])) {
+                SideDir d = side_dir(sigma_mu - I.mv[M_RC][i] * I.mv[M_BC][i] , I.mv[M_BC][i], I.mv[M_RC][i], I.mv[M_I4][i], -jd, delta);
+                I.mv[M_RC][i] += alpha * d.ds; I.mv[M_BC][i] += alpha * d.dz; I.mv[M_I4][i] += alpha * (-jd + d.ds);
             }
         });
         for_n(T, N, [&](int j) {
-            double xj = x[j], dj = dx[j];
-            if (xl[j] == xu[j]) { yx[j] += alpha * (dj + rxu[j]) / delta; rxu[j] += alpha * dj; x[j] = xj + alpha * dj; return; }
-            if (!isinf(xu[j])) {
-                SideDir d = side_dir(sigma_mu - sxu[j] * zxu[j] , zxu[j], sxu[j], rxu[j], dj, delta);
-                sxu[j] += alpha * d.ds; zxu[j] += alpha * d.dz; rxu[j] += alpha * (dj + d.ds);
+            double xj = I.nv[N_X][j], dj = I.nv[N_XT][j];
+            if (I.nv[N_XL][j] == I.nv[N_XU][j]) { I.nv[N_MASK][j] += alpha * (dj + I.nv[N_TMP2][j]) / delta; I.nv[N_TMP2][j] += alpha * dj; I.nv[N_X][j] = xj + alpha * dj; return; }
+            if (!isinf(I.nv[N_XU][j])) {
+                SideDir d = side_dir(sigma_mu - I.nv[N_ZB][j] * I.nv[N_YB][j] , I.nv[N_YB][j], I.nv[N_ZB][j], I.nv[N_TMP2][j], dj, delta);
+                I.nv[N_ZB][j] += alpha * d.ds; I.nv[N_YB][j] += alpha * d.dz; I.nv[N_TMP2][j] += alpha * (dj + d.ds);
             }
-            if (!isinf(xl[j])) {
-                SideDir d = side_dir(sigma_mu - sxl[j] * zxl[j] , zxl[j], sxl[j], rxl[j], -dj, delta);
-                sxl[j] += alpha * d.ds; zxl[j] += alpha * d.dz; rxl[j] += alpha * (-dj + d.ds);
+            if (!isinf(I.nv[N_XL][j])) {
+                SideDir d = side_dir(sigma_mu - I.nv[N_RB][j] * I.nv[N_KP][j] , I.nv[N_KP][j], I.nv[N_RB][j], I.nv[N_I1][j], -dj, delta);
+                I.nv[N_RB][j] += alpha * d.ds; I.nv[N_KP][j] += alpha * d.dz; I.nv[N_I1][j] += alpha * (-dj + d.ds);
             }
-            x[j] = xj + alpha * dj;
+            I.nv[N_X][j] = xj + alpha * dj;
         });
         delta = fmax(o.ipm_delta_min, delta * 0.3);
         if (rho_p > o.ipm_rho0) rho_p = fmax(o.ipm_rho0, rho_p / 3.0);
@@ -406,8 +398,8 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
     if (out.solved || out.almost) {
         // multipliers in the OSQP sign the output stage expects: yc (rows) and yb (box)
         double *yc = I.mv[M_YC], *yb = I.nv[N_YB];
-        for_n(T, M, [&](int i) { yc[i] = (rl[i] == ru[i]) ? y[i] : (zru[i] - zrl[i]); });
-        for_n(T, N, [&](int j) { yb[j] = (xl[j] == xu[j]) ? yx[j] : (zxu[j] - zxl[j]); });
+        for_n(T, M, [&](int i) { yc[i] = (I.mv[M_RL][i] == I.mv[M_RU][i]) ? I.mv[M_I1][i] : (I.mv[M_YC][i] - I.mv[M_BC][i]); });
+        for_n(T, N, [&](int j) { yb[j] = (I.nv[N_XL][j] == I.nv[N_XU][j]) ? I.nv[N_MASK][j] : (I.nv[N_YB][j] - I.nv[N_KP][j]); });
         T.sync();
     }
     return out;
