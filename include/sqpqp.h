@@ -157,8 +157,15 @@ int sqpqp_device_outputs(sqpqp_handle h, double** p, double** lambda, double** m
                          sqpqp_info** info);
 int sqpqp_fetch_info(sqpqp_handle h, sqpqp_info* info);
 /* Size of the shared symbolic Cholesky factor of the condensed Newton matrix (0 if unavailable):
- * nnz(L), elimination-tree levels, flops per numeric factorisation. */
+ * nnz(L), level-scheduled (sparse) elimination-tree levels, flops of the sparse part per numeric
+ * factorisation. */
 int sqpqp_chol_stats(sqpqp_handle h, int64_t* nnzL, int64_t* nlev, int64_t* flops);
+/* Layout of that factor: columns of the dense tail (top of the elimination tree, factorised as a
+ * packed dense matrix in shared memory; 0 = none) and levels of the whole elimination tree. */
+int sqpqp_chol_layout(sqpqp_handle h, int64_t* tail_cols, int64_t* tree_levels);
+/* Development aid: cycles per solve segment summed over CTAs since the last call (32 counters; all
+ * zero unless the library was built with -DSQPQP_PROF). */
+int sqpqp_prof_read(sqpqp_handle h, uint64_t* out32);
 /* Number of slack columns S (order: for each row i > m_lin: u_i, then v_i if two-sided). */
 int sqpqp_num_slacks(sqpqp_handle h, int32_t* S);
 

@@ -16,7 +16,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libsqpqp.so")
+PROF_BUILD = os.environ.get("SQPQP_PROF") == "1"  # development build with the in-kernel phase profile
+LIB_PATH = os.path.join(CSRC, "libsqpqp_prof.so" if PROF_BUILD else "libsqpqp.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "sqpqp.h")
 
 NVCC_FLAGS = [
@@ -81,17 +82,18 @@ EXPORTS = [
     "sqpqp_setup_nlp", "sqpqp_update_nlp", "sqpqp_update_nlp_device", "sqpqp_solve_tr", "sqpqp_num_slacks",
     "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
     "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
-    "sqpqp_fetch_info", "sqpqp_chol_stats",
+    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read",
 ]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/sqpqp.cu for sm_100a with nvcc (cross-compiles without a GPU)."""
+    """Compile csrc/sqpqp.cu for sm_100a with nvcc (cross-compiles without a GPU).
+    SQPQP_PROF=1 in the environment adds the in-kernel phase profile (development builds only)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [HEADER]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "sqpqp.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-DSQPQP_PROF"] if PROF_BUILD else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "sqpqp.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
@@ -135,6 +137,8 @@ def lib():
     L.sqpqp_device_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.sqpqp_fetch_info.argtypes = [vp, C.c_void_p]
     L.sqpqp_chol_stats.argtypes = [vp, _lp, _lp, _lp]
+    L.sqpqp_chol_layout.argtypes = [vp, _lp, _lp]
+    L.sqpqp_prof_read.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.sqpqp_num_slacks.argtypes = [vp, _ip]
     L.sqpqp_merit.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp]
     L.sqpqp_kt_residuals.argtypes = [vp, _dp, _dp, _dp, _dp]
@@ -278,7 +282,15 @@ class Engine:
     def chol_stats(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         self._ck(self.L.sqpqp_chol_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"nnzL": a.value, "levels": b.value, "flops": c.value}
+        t, lv = C.c_int64(), C.c_int64()
+        self._ck(self.L.sqpqp_chol_layout(self.h, C.byref(t), C.byref(lv)))
+        return {"nnzL": a.value, "levels": b.value, "flops": c.value, "dense_tail": t.value, "tree_levels": lv.value}
+
+    def prof_read(self):
+        """Cycles per solve segment (csrc/common.cuh ProfSeg) since the last call; zeros in a normal build."""
+        out = (C.c_uint64 * 32)()
+        self._ck(self.L.sqpqp_prof_read(self.h, out))
+        return np.array(list(out), dtype=np.uint64)
 
     @property
     def stream(self):

@@ -26,6 +26,25 @@ struct DevOpts {
     sqpqp_options o;
 };
 
+// A work-vector slot resolved to its address at the point of use, from kernel parameters (constant
+// bank) only: base[k] + instance offset, or the CTA's shared-memory copy when the slot is resident.
+// (A per-thread table of the ~40 resolved pointers does not fit the 64-register budget of the
+// 4-CTAs-per-SM build: it lived in local memory and its reloads were 20 % of all load instructions
+// and the larger part of the kernel's DRAM traffic -- profiles/r01_ncu_summary.md.)
+struct VecTab {
+    double* const* base;
+    const int* off;   // shared-memory offsets (doubles) or nullptr
+    double* dsm;
+    size_t inst_off;
+    __device__ __forceinline__ double* operator[](int k) const {
+        if (off) {
+            int o = off[k];
+            if (o >= 0) return dsm + o;
+        }
+        return base[k] + inst_off;
+    }
+};
+
 // resolved per-instance views
 struct Inst {
     int N, M;            // active columns / rows this phase
@@ -36,8 +55,7 @@ struct Inst {
     int lgJ, lgT, lgH;
     const double *Jv, *Tv, *Hv;
     double *Jsv, *Tsv, *Hsv;
-    double* nv[N_COUNT];
-    double* mv[M_COUNT];
+    VecTab nv, mv;
     signed char *codeC, *codeB, *prevC, *prevB, *triedC, *triedB;
 };
 
@@ -175,13 +193,15 @@ struct IpmOut {
     double rp, rd, rho_p;
 };
 template <class Team>
-__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval, double* yw, const sqpqp_options& o,
+__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, const sqpqp_options& o,
                           double c, int phase, const double* xk_scaled_start);
 
 // ---------------------------------------------------------------------------------------
 template <class Team>
 __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, int inst, int phase,
                                const Placement* pl, double* dsm) {
+    Prof pfo;
+    pfo.start();
     Inst I;
     I.n = P.n; I.m = P.m; I.S = P.S;
     I.M = P.m;
@@ -196,13 +216,10 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     I.lgH = P.lgH;
     I.Jv = P.Jv + (size_t)inst * P.nnzJ; I.Tv = P.Tv + (size_t)inst * P.nnzT; I.Hv = P.Hv + (size_t)inst * P.nnzH;
     I.Jsv = P.Jsv + (size_t)inst * P.nnzJ; I.Tsv = P.Tsv + (size_t)inst * P.nnzT; I.Hsv = P.Hsv + (size_t)inst * P.nnzH;
-    for (int k = 0; k < N_COUNT; ++k) I.nv[k] = P.nv[k] + (size_t)inst * P.Ne;
-    for (int k = 0; k < M_COUNT; ++k) I.mv[k] = P.mv[k] + (size_t)inst * P.m;
-    if (pl) {  // scratch arrays resident in this CTA's shared memory for the whole solve
-        for (int k = 0; k < N_COUNT; ++k)
-            if (pl->n_off[k] >= 0) I.nv[k] = dsm + pl->n_off[k];
-        for (int k = 0; k < M_COUNT; ++k)
-            if (pl->m_off[k] >= 0) I.mv[k] = dsm + pl->m_off[k];
+    const bool resident = pl && pl->vec_resident;  // scratch arrays resident in this CTA's shared memory for the whole solve
+    I.nv = VecTab{P.nv, resident ? pl->n_off : (const int*)nullptr, dsm, (size_t)inst * P.Ne};
+    I.mv = VecTab{P.mv, resident ? pl->m_off : (const int*)nullptr, dsm, (size_t)inst * P.m};
+    if (resident) {
         if (pl->jsv >= 0) I.Jsv = dsm + pl->jsv;
         if (pl->tsv >= 0) I.Tsv = dsm + pl->tsv;
         if (pl->hsv >= 0) I.Hsv = dsm + pl->hsv;
@@ -335,17 +352,26 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     const bool fr = phase == SQPQP_PHASE_FR;
     if ((fr ? P.has_chol_fr : P.has_chol) && o.method != 1) {
         const CholDev& CD = fr ? P.chol_fr : P.chol;
-        double* Lv = fr ? P.Lval_fr + (size_t)inst * CD.nnzL : P.Lval + (size_t)inst * CD.nnzL;
-        double* ywp = fr ? P.yw_fr + (size_t)inst * P.Ne : P.yw + (size_t)inst * P.n;
-        if (pl && pl->lval >= 0) Lv = dsm + pl->lval;
-        if (pl && pl->yw >= 0) ywp = dsm + pl->yw;
+        CholWork W;
+        W.L = fr ? P.Lval_fr + (size_t)inst * CD.nnzL : P.Lval + (size_t)inst * CD.nnzL;
+        W.yw = fr ? P.yw_fr + (size_t)inst * P.Ne : P.yw + (size_t)inst * P.n;
+        W.dinv = fr ? P.dinv_fr + (size_t)inst * P.Ne : P.dinv + (size_t)inst * P.n;
+        W.D = W.col = nullptr;
+        if (pl) {  // shared-memory parts of the factorisation (the dense tail lives nowhere else)
+            if (pl->lval >= 0) W.L = dsm + pl->lval;
+            if (pl->yw >= 0) W.yw = dsm + pl->yw;
+            if (pl->dinv >= 0) W.dinv = dsm + pl->dinv;
+            if (pl->dtail >= 0) { W.D = dsm + pl->dtail; W.col = dsm + pl->dcol; }
+        }
         const double* start = nullptr;
         if (phase == SQPQP_PHASE_LP) {
             for_n(T, N, [&](int j) { x[j] = xk[j] / D[j]; });
             T.sync();
             start = x;
         }
-        IpmOut io = ipm_run(T, I, CD, Lv, ywp, o, c, phase, start);
+        pfo.lap(PS_PROLOGUE);
+        IpmOut io = ipm_run(T, I, CD, W, o, c, phase, start);
+        pfo.start();
         ipm_iters = io.iters;
         nfact = io.nfact;
         ipm_blowup = io.blowup;
@@ -737,6 +763,7 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
         inf.chol_factorizations = nfact;
     }
     T.sync();
+    pfo.lap(PS_EPILOGUE);
 }
 
 // ---- kernels ---------------------------------------------------------------------------
@@ -744,7 +771,8 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
 // one-CTA-per-SM resident configuration; <256,4> and <128,8> cap registers at 64 so that many
 // instances share an SM and hide each other's (L2-latency-bound) level-scheduled phases.
 template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(Prob P, DevOpts O, int phase, Placement pl) {
+__global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(const __grid_constant__ Prob P, const __grid_constant__ DevOpts O, int phase,
+                                                          const __grid_constant__ Placement pl) {
     __shared__ double sh[2 * SQPQP_MAX_RED * 32];
     extern __shared__ double dsm[];
     for (int inst = blockIdx.x; inst < P.batch; inst += gridDim.x) {
@@ -755,7 +783,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(Prob P, DevOpts O, int
     }
 }
 
-__global__ void __launch_bounds__(256) k_solve_grid(Prob P, DevOpts O, int phase) {
+__global__ void __launch_bounds__(256) k_solve_grid(const __grid_constant__ Prob P, const __grid_constant__ DevOpts O, int phase) {
     __shared__ double sh[SQPQP_MAX_RED * 32];
     GridTeam T(sh, P.gred, P.gred_stride);
     for (int inst = 0; inst < P.batch; ++inst) {

@@ -36,15 +36,30 @@ struct Csr {
     const int* col;  // [nnz]
 };
 
-// device view of the symbolic Cholesky analysis (symbolic.hpp); all arrays shared by the batch
+// device view of the symbolic Cholesky analysis (symbolic.hpp); all arrays shared by the batch.
+// Columns are numbered level-major: sparse level l = columns lev_ptr[l] .. lev_ptr[l+1]-1, then the
+// dense tail n0 .. n-1 (T columns, factorised as a packed dense matrix in shared memory).
 struct CholDev {
-    int n, nnzL, nlev;
+    int n, nnzL, nlev, n0, T;
     const int *perm;
     const int *Lp, *Li;
-    const int *Rp, *Rc, *Ri;
-    const int *lev_ptr, *lev_cols;
-    const int *fd_ptr, *fo_ptr, *f_ent, *fp_ptr, *fp_a, *fp_b, *ent_diag;
-    const int *as_ptr, *as_a, *as_b, *as_r, *as_h, *as_d;
+    const int *Rp, *Rmid;
+    const int2 *Rci;       // (value index, column) of the strictly-lower CSR
+    const int *lev_ptr;
+    const int *fp_ptr;
+    const int2 *fp_ab;     // pairs of value indices
+    const int *tpos;       // packed tail position of the tail entries
+    const int4 *as_hd;     // per entry: (P value index | -1, d index | -1, term begin, term end)
+    const int4 *as_abr;    // per term: (Jv a, Jv b, weight row, 0)
+};
+
+// per-instance numeric state of the factorisation, resolved for one team
+struct CholWork {
+    double* L;      // [nnzL] factor values (global / L2; tail entries hold the assembled K only)
+    double* D;      // [T(T+1)/2] dense tail, packed row-major lower triangle (shared memory)
+    double* col;    // [T] scaled pivot column of the dense factorisation (shared memory)
+    double* dinv;   // [n] 1 / L_jj
+    double* yw;     // [n] triangular-solve scratch in permuted order
 };
 
 struct Prob {
@@ -80,6 +95,7 @@ struct Prob {
     CholDev chol_fr;   // feasibility-restoration LP: n + S columns ([J|S]), P = 0
     int has_chol, has_chol_fr;
     double *Lval, *yw, *Lval_fr, *yw_fr;
+    double *dinv, *dinv_fr;   // [batch][n], [batch][Ne] (used when the shared-memory budget cannot hold them)
     // grid-team reduction scratch: [2][SQPQP_MAX_RED][maxblocks]
     double* gred;
     int gred_stride;
@@ -93,8 +109,35 @@ struct Placement {
     int m_off[M_COUNT];
     int jsv, tsv, hsv;
     int lval, yw;
+    int dtail, dcol, dinv;  // dense tail of the factor, its pivot column, inverse diagonal (interior-point path)
+    int vec_resident;       // 1 if any work vector / matrix value array is placed (else only the factorisation parts)
     int total;  // doubles
 };
+
+// ---- optional in-kernel phase profile (build with -DSQPQP_PROF; tools/gpu_prof.py) ----------------
+// Thread 0 of every CTA adds the clock64 cycles it spent in each segment of the solve to a global
+// table; the sum over CTAs gives the share of CTA-time per segment.  Compiled out by default.
+enum ProfSeg {
+    PS_PROLOGUE = 0, PS_RESID, PS_WEIGHTS, PS_ASSEMBLE, PS_FACTOR_SPARSE, PS_SCHUR, PS_FACTOR_DENSE, PS_RHS, PS_FWD, PS_TAIL,
+    PS_BWD, PS_RATIO, PS_UPDATE, PS_EPILOGUE, PS_OTHER, PS_COUNT
+};
+#ifdef SQPQP_PROF
+__device__ unsigned long long g_prof[32];
+struct Prof {
+    long long t0;
+    __device__ __forceinline__ void start() { t0 = clock64(); }
+    __device__ __forceinline__ void lap(int k) {
+        long long t = clock64();
+        if (threadIdx.x == 0) atomicAdd(&g_prof[k], (unsigned long long)(t - t0));
+        t0 = t;
+    }
+};
+#else
+struct Prof {
+    __device__ __forceinline__ void start() {}
+    __device__ __forceinline__ void lap(int) {}
+};
+#endif
 
 #define CUDA_OK(call)                                                       \
     do {                                                                     \

@@ -34,7 +34,7 @@ __device__ __forceinline__ SideDir side_dir(double rc, double z, double s, doubl
 __device__ __forceinline__ double step_ratio(double v, double dv) { return dv < 0.0 ? -dv / v : 0.0; }
 
 template <class Team>
-__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval, double* yw, const sqpqp_options& o,
+__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, const sqpqp_options& o,
                           double c, int phase, const double* xk_scaled_start) {
     const int N = I.N, M = I.M;
     // Work vectors are addressed through the (shared-memory resident) pointer table of `I` at every use
@@ -45,6 +45,8 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
     // delta ~ 1e-8 and a freshly evaluated residual carries ~1e-16 |Ax| of rounding noise, which the
     // dual update dy = (J dx + r)/delta would amplify by 1/delta.
     IpmOut out{false, false, false, false, 0, 0, INFINITY, INFINITY, 0.0};
+    Prof pf;
+    pf.start();
     // ---- start point: I.nv[N_X] inside the box, unit duals, slacks >= 1 --------------------------------
     for_n(T, N, [&](int j) {
         double v = xk_scaled_start ? xk_scaled_start[j] : 0.0;
@@ -186,6 +188,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
         if (o.verbose && T.tid() == 0)
             printf("  ipm %3d rp=%.2e rd=%.2e mu=%.2e delta=%.1e rho=%.1e nfact=%d\n", it, out.rp, out.rd, mu / c, delta, rho_p, out.nfact);
         if (!(mu == mu) || !(out.rd == out.rd)) break;  // NaN guard
+        pf.lap(PS_RESID);
         // ---- barrier update: shrink mu_t while the current barrier problem is solved to kappa*mu_t ---
         for (int g = 0; g < 60; ++g) {
             double comp = fmax(fabs(sz[0] - mu_t), fabs(-sz[1] - mu_t));
@@ -217,8 +220,10 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
                 I.nv[N_DSH][j] = wj + rho_p + (I.useH ? 0.0 : I.nv[N_HD][j]);
             });
             T.sync();
-            chol_assemble(T, C, Lval, I.useH ? I.Hsv : (const double*)nullptr, I.nv[N_DSH], I.mv[M_RW], I.Jsv);
-            fact_ok = chol_factor(T, C, Lval);
+            pf.lap(PS_WEIGHTS);
+            chol_assemble(T, C, W, I.useH ? I.Hsv : (const double*)nullptr, I.nv[N_DSH], I.mv[M_RW], I.Jsv);
+            pf.lap(PS_ASSEMBLE);
+            fact_ok = chol_factor(T, C, W, pf);
             ++out.nfact;
             if (!fact_ok) rho_p = fmax(fmax(10.0 * rho_p, rho_last > 0.0 ? rho_last / 3.0 : 1e-4), 1e-6);
             if (rho_p > 1e8) break;
@@ -266,7 +271,8 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
                 I.nv[N_P][j] = -I.nv[N_R][j] - tt - tb;
             });
             T.sync();
-            chol_solve(T, C, Lval, I.nv[N_P], I.nv[N_XT], yw);
+            pf.lap(PS_RHS);
+            chol_solve(T, C, W, I.nv[N_P], I.nv[N_XT], pf);
             // iterative refinement against the matrix-free K (K is ill-conditioned by design)
             for (int rf = 0; rf < o.ipm_refine; ++rf) {
                 apply_K(T, I, I.nv[N_XT], I.nv[N_TMP], I.nv[N_DSH], I.mv[M_RW], (const double*)nullptr);
@@ -285,7 +291,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
                     if (T.tid() == 0) printf("      pass %d refine %d: |I.nv[N_P] - K I.nv[N_XT]| = %.2e  |I.nv[N_P]| = %.2e\n", pass, rf, nr[0], nr[1]);
                 }
                 T.sync();
-                chol_solve(T, C, Lval, I.nv[N_TMP], I.nv[N_TMP], yw);
+                chol_solve(T, C, W, I.nv[N_TMP], I.nv[N_TMP], pf);
                 for_n(T, N, [&](int j) { I.nv[N_XT][j] += I.nv[N_TMP][j]; });
                 T.sync();
             }
@@ -362,6 +368,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
                 if (o.verbose && T.tid() == 0) printf("      sigma_mu=%.2e alpha=%.3e\n", sigma_mu / c, alpha);
             }
         }
+        pf.lap(PS_RATIO);
         // ---- update with the corrector direction -------------------------------------------------------
         for_n(T, M, [&](int i) {
             double ax = I.mv[M_I3][i], jd = I.mv[M_I2][i];
@@ -389,6 +396,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, double* Lval
             }
             I.nv[N_X][j] = xj + alpha * dj;
         });
+        pf.lap(PS_UPDATE);
         delta = fmax(o.ipm_delta_min, delta * 0.3);
         if (rho_p > o.ipm_rho0) rho_p = fmax(o.ipm_rho0, rho_p / 3.0);
         out.iters = it + 1;

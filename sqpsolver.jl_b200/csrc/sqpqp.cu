@@ -50,7 +50,8 @@ struct sqpqp_handle_s {
     double last_ms = 0.0;
     bool timing_pending = false;
     int num_sms = 148, coop_blocks = 0, max_dyn_smem = 0;
-    int chol_nnzL = 0, chol_nlev = 0;
+    int chol_nnzL = 0, chol_nlev = 0, chol_tail = 0, chol_nlev_total = 0;
+    int cta4_smem = 48 * 1024;  // dynamic shared memory of one CTA when four share an SM
     int64_t chol_flops = 0;
     std::vector<double> avg_row;  // avg row length of J(normal), J(ext), T, H
     // generic-lane bookkeeping
@@ -242,7 +243,13 @@ extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
     h->max_dyn_smem = optin - 4096 - 1024;  // static reduction scratch + slack
     if (h->max_dyn_smem < 0) h->max_dyn_smem = 0;
     cudaFuncSetAttribute(k_solve_cta<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
-    cudaFuncSetAttribute(k_solve_cta<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+    {   // four CTAs per SM: (SM shared memory - 4 x (static scratch + 1 KB system reservation)) / 4
+        int per_sm = 0;
+        cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+        int v = (per_sm / 4 - 4096 - 1024) & ~1023;
+        h->cta4_smem = v < 16 * 1024 ? 16 * 1024 : v;
+    }
+    cudaFuncSetAttribute(k_solve_cta<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta4_smem);
     cudaFuncSetAttribute(k_solve_cta<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024);
     *out = h;
     return 0;
@@ -297,6 +304,29 @@ extern "C" int sqpqp_chol_stats(sqpqp_handle h, int64_t* nnzL, int64_t* nlev, in
     if (nnzL) *nnzL = h->P.has_chol ? h->chol_nnzL : 0;
     if (nlev) *nlev = h->P.has_chol ? h->chol_nlev : 0;
     if (flops) *flops = h->P.has_chol ? h->chol_flops : 0;
+    return 0;
+}
+
+// Development aid (tools/gpu_prof.py): read and clear the in-kernel phase profile; all zeros unless
+// the library was built with -DSQPQP_PROF.
+extern "C" int sqpqp_prof_read(sqpqp_handle h, uint64_t* out32) {
+    if (!h || !out32) return SQPQP_E_BADARG;
+    memset(out32, 0, 32 * sizeof(uint64_t));
+#ifdef SQPQP_PROF
+    DeviceGuard g(h->device);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaMemcpyFromSymbol(out32, g_prof, 32 * sizeof(uint64_t)));
+    uint64_t z[32] = {0};
+    CUDA_OK(cudaMemcpyToSymbol(g_prof, z, sizeof(z)));
+#endif
+    return 0;
+}
+
+extern "C" int sqpqp_chol_layout(sqpqp_handle h, int64_t* tail_cols, int64_t* tree_levels) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    if (tail_cols) *tail_cols = h->P.has_chol ? h->chol_tail : 0;
+    if (tree_levels) *tree_levels = h->P.has_chol ? h->chol_nlev_total : 0;
     return 0;
 }
 
@@ -455,38 +485,52 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             return 0;
         };
         auto upload_symbolic = [&](const Symbolic& Sy, CholDev& C, int ncols) -> int {
-            C.n = ncols; C.nnzL = Sy.nnzL; C.nlev = Sy.nlev;
-            const std::vector<int>* srcs[] = {&Sy.perm, &Sy.Lp, &Sy.Li, &Sy.Rp, &Sy.Rc, &Sy.Ri, &Sy.lev_ptr, &Sy.lev_cols, &Sy.fd_ptr,
-                                              &Sy.fo_ptr, &Sy.f_ent, &Sy.fp_ptr, &Sy.fp_a, &Sy.fp_b, &Sy.ent_diag, &Sy.as_ptr,
-                                              &Sy.as_a, &Sy.as_b, &Sy.as_r, &Sy.as_h, &Sy.as_d};
-            const int** dsts[] = {&C.perm, &C.Lp, &C.Li, &C.Rp, &C.Rc, &C.Ri, &C.lev_ptr, &C.lev_cols, &C.fd_ptr, &C.fo_ptr,
-                                  &C.f_ent, &C.fp_ptr, &C.fp_a, &C.fp_b, &C.ent_diag, &C.as_ptr, &C.as_a, &C.as_b, &C.as_r,
-                                  &C.as_h, &C.as_d};
-            for (int k = 0; k < 21; ++k) {
-                int rc2 = up(*srcs[k], dsts[k]);
+            C.n = ncols; C.nnzL = Sy.nnzL; C.nlev = Sy.nlev; C.n0 = Sy.n0; C.T = Sy.T;
+            const std::vector<int>* srcs[] = {&Sy.perm, &Sy.Lp, &Sy.Li, &Sy.Rp, &Sy.Rmid, &Sy.Rci, &Sy.lev_ptr, &Sy.fp_ptr,
+                                              &Sy.fp_ab, &Sy.tpos, &Sy.as_hd, &Sy.as_abr};
+            const int** dsts[] = {&C.perm, &C.Lp, &C.Li, &C.Rp, &C.Rmid, (const int**)&C.Rci, &C.lev_ptr, &C.fp_ptr,
+                                  (const int**)&C.fp_ab, &C.tpos, (const int**)&C.as_hd, (const int**)&C.as_abr};
+            for (int k = 0; k < 12; ++k) {
+                int rc2 = up(*srcs[k], dsts[k]);  // cudaMalloc alignment (256 B) covers the int2 / int4 views
                 if (rc2) return rc2;
             }
             return 0;
         };
+        // Dense tail of the factor (chol.cuh): as many top levels of the elimination tree as fit the
+        // shared memory one CTA gets when four CTAs share an SM, next to the inverse diagonal and the
+        // solve scratch when those fit as well.  A single large instance runs on the cooperative grid
+        // (no CTA-local shared memory across the team) and keeps the plain level-scheduled code.
+        auto tail_cap = [&](int ncols) -> int {
+            if (batch == 1 && (size_t)P.Ne + m > 6000) return 0;
+            size_t cap = (size_t)h->cta4_smem / sizeof(double);
+            size_t vec = 2 * (size_t)((ncols + 1) & ~1);
+            if (vec <= cap / 2) cap -= vec;
+            int t = 0;
+            while (t < 128 && (size_t)(t + 1) * (t + 2) / 2 + (size_t)((t + 2) & ~1) <= cap) ++t;
+            return t;
+        };
         CUDA_OK(cudaStreamSynchronize(h->stream));
-        Symbolic Sy = symbolic_analyze(n, m, hJrb.data(), hJre.data(), hJc.data(), hHrp.data(), hHc.data());
-        if (Sy.ok && (int64_t)Sy.fp_a.size() < ((int64_t)1 << 28)) {
+        Symbolic Sy = symbolic_analyze(n, m, hJrb.data(), hJre.data(), hJc.data(), hHrp.data(), hHc.data(), 512, tail_cap(n));
+        if (Sy.ok && (int64_t)Sy.fp_ab.size() < ((int64_t)1 << 29)) {
             int rc2 = upload_symbolic(Sy, P.chol, n);
             if (rc2) return rc2;
             DALLOC(P.Lval, B * (size_t)Sy.nnzL);
             DALLOC(P.yw, B * (size_t)n);
+            DALLOC(P.dinv, B * (size_t)n);
             P.has_chol = 1;
-            h->chol_nnzL = Sy.nnzL; h->chol_nlev = Sy.nlev; h->chol_flops = Sy.flops;
+            h->chol_nnzL = Sy.nnzL; h->chol_nlev = Sy.nlev; h->chol_flops = Sy.flops; h->chol_tail = Sy.T;
+            h->chol_nlev_total = Sy.nlev_total;
         }
         // feasibility-restoration LP: columns [J | S], no quadratic term
         P.has_chol_fr = 0;
         if (S > 0 && m > 0) {
-            Symbolic Sf = symbolic_analyze(P.Ne, m, hJrb.data(), hJrb.data() + 1, hJc.data(), nullptr, nullptr);
-            if (Sf.ok && (int64_t)Sf.fp_a.size() < ((int64_t)1 << 28)) {
+            Symbolic Sf = symbolic_analyze(P.Ne, m, hJrb.data(), hJrb.data() + 1, hJc.data(), nullptr, nullptr, 512, tail_cap(P.Ne));
+            if (Sf.ok && (int64_t)Sf.fp_ab.size() < ((int64_t)1 << 29)) {
                 int rc2 = upload_symbolic(Sf, P.chol_fr, P.Ne);
                 if (rc2) return rc2;
                 DALLOC(P.Lval_fr, B * (size_t)Sf.nnzL);
                 DALLOC(P.yw_fr, B * (size_t)P.Ne);
+                DALLOC(P.dinv_fr, B * (size_t)P.Ne);
                 P.has_chol_fr = 1;
             }
         }
@@ -568,36 +612,46 @@ extern "C" int sqpqp_update_nlp_device(sqpqp_handle h, const double* dE, const d
 // Greedy shared-memory placement, hottest arrays first: the PCG working set (6 N-vectors +
 // 2 M-vectors), then the scaled matrix values (read 3x per PCG iteration), then the ADMM
 // iterates, then the polish scratch.  Warm-start vectors must survive the kernel and stay global.
-static void place_arrays(const Prob& P, int phase, size_t budget_bytes, bool ipm, Placement* pl) {
+static void place_arrays(const Prob& P, int phase, size_t budget_bytes, bool ipm, bool vectors, Placement* pl) {
     const int N = (phase == SQPQP_PHASE_FR) ? P.Ne : P.n, M = P.m > 0 ? P.m : 1;
     for (int k = 0; k < N_COUNT; ++k) pl->n_off[k] = -1;
     for (int k = 0; k < M_COUNT; ++k) pl->m_off[k] = -1;
-    pl->jsv = pl->tsv = pl->hsv = pl->lval = pl->yw = -1;
+    pl->jsv = pl->tsv = pl->hsv = pl->lval = pl->yw = pl->dtail = pl->dcol = pl->dinv = -1;
+    pl->vec_resident = 0;
     size_t cap = budget_bytes / sizeof(double), off = 0;
     auto take = [&](int* slot, size_t len) {
         len = (len + 1) & ~(size_t)1;  // keep 16-byte alignment
         if (off + len <= cap) { *slot = (int)off; off += len; }
     };
-    if (ipm) {  // interior point: the factor and the triangular-solve scratch are the hot data
-        const bool fr = phase == SQPQP_PHASE_FR;
-        take(&pl->yw, fr ? P.Ne : P.n);
-        take(&pl->lval, fr ? P.chol_fr.nnzL : P.chol.nnzL);
+    if (ipm) {  // interior point: the dense tail of the factor (lives only here), then the solve scratch
+        const CholDev& C = (phase == SQPQP_PHASE_FR) ? P.chol_fr : P.chol;
+        if (C.T > 0) {
+            take(&pl->dtail, (size_t)C.T * (C.T + 1) / 2);
+            take(&pl->dcol, C.T);
+        }
+        take(&pl->dinv, C.n);
+        take(&pl->yw, C.n);
+        if (vectors) take(&pl->lval, C.nnzL);
     }
-    const int hotN[] = {N_P, N_KP, N_R, N_XT, N_MINV, N_DSH};
-    for (int k : hotN) take(&pl->n_off[k], N);
-    take(&pl->m_off[M_T], M);
-    take(&pl->m_off[M_RC], M);
-    take(&pl->tsv, P.nnzT);
-    take(&pl->jsv, P.nnzJ);
-    if (phase == SQPQP_PHASE_QP || phase == SQPQP_PHASE_SOC) take(&pl->hsv, P.nnzH);
-    const int warmN[] = {N_X, N_ZB, N_YB, N_RB, N_Q, N_XL, N_XU, N_HD, N_D};
-    const int warmM[] = {M_ZC, M_YC, M_RL, M_RU, M_ES, M_AX};
-    for (int k : warmN) take(&pl->n_off[k], N);
-    for (int k : warmM) take(&pl->m_off[k], M);
-    const int coldN[] = {N_MASK, N_XFIX, N_TMP, N_TMP2};
-    const int coldM[] = {M_RW, M_BC, M_YP, M_TMP};
-    for (int k : coldN) take(&pl->n_off[k], N);
-    for (int k : coldM) take(&pl->m_off[k], M);
+    if (vectors) {
+        size_t before = off;
+        const int hotN[] = {N_P, N_KP, N_R, N_XT, N_MINV, N_DSH};
+        for (int k : hotN) take(&pl->n_off[k], N);
+        take(&pl->m_off[M_T], M);
+        take(&pl->m_off[M_RC], M);
+        take(&pl->tsv, P.nnzT);
+        take(&pl->jsv, P.nnzJ);
+        if (phase == SQPQP_PHASE_QP || phase == SQPQP_PHASE_SOC) take(&pl->hsv, P.nnzH);
+        const int warmN[] = {N_X, N_ZB, N_YB, N_RB, N_Q, N_XL, N_XU, N_HD, N_D};
+        const int warmM[] = {M_ZC, M_YC, M_RL, M_RU, M_ES, M_AX};
+        for (int k : warmN) take(&pl->n_off[k], N);
+        for (int k : warmM) take(&pl->m_off[k], M);
+        const int coldN[] = {N_MASK, N_XFIX, N_TMP, N_TMP2};
+        const int coldM[] = {M_RW, M_BC, M_YP, M_TMP};
+        for (int k : coldN) take(&pl->n_off[k], N);
+        for (int k : coldM) take(&pl->m_off[k], M);
+        pl->vec_resident = off > before;
+    }
     pl->total = (int)off;
 }
 
@@ -616,6 +670,7 @@ static int launch_solve(sqpqp_handle h, int phase) {
     DevOpts O{h->opts};
     int team = h->opts.team;
     if (team == 0) team = (B == 1 && (size_t)P.Ne + P.m > 6000) ? 2 : 1;
+    if (team == 2 && ((phase == SQPQP_PHASE_FR ? P.chol_fr.T : P.chol.T) > 0)) team = 1;  // dense tail needs CTA shared memory
     CUDA_OK(cudaEventRecord(h->ev0, h->stream));
     if (team == 2) {
         void* args[] = {(void*)&P, (void*)&O, (void*)&phase};
@@ -623,21 +678,31 @@ static int launch_solve(sqpqp_handle h, int phase) {
     } else {
         int threads = pick_threads(h, phase);
         int grid = (int)(B < 65535 ? B : 65535);
-        // shared-memory budget: everything (1 CTA/SM) unless the batch needs co-residency
-        size_t budget = (size_t)(h->opts.smem_kb < 0 ? 0 : h->opts.smem_kb) * 1024;
-        // large batches: several CTAs share an SM and hide each other's latency; the shared index
-        // programs of the factorisation are re-read through L1, so L1 capacity beats residency
-        // (measured, profiles/r01_tuning.md).  Small batches: one CTA per SM, everything resident.
+        // Shared memory: the factorisation's dense tail, inverse diagonal and solve scratch always; the
+        // work vectors and matrix values only when one CTA owns the SM (small batches).  Large batches:
+        // several CTAs share an SM and hide each other's latency, and the shared index programs are
+        // re-read through L1, so L1 capacity beats vector residency (measured, profiles/r01_tuning.md).
         const bool many = B >= (size_t)2 * h->num_sms;
-        if (h->opts.smem_kb < 0) budget = many ? 0 : (size_t)h->max_dyn_smem;
-        if (!h->opts.threads && many && threads > 256) threads = 256;
-        if (budget > (size_t)h->max_dyn_smem) budget = h->max_dyn_smem;
-        Placement pl;
-        bool ipm = (phase == SQPQP_PHASE_FR ? P.has_chol_fr : P.has_chol) && h->opts.method != 1;
-        place_arrays(P, phase, budget, ipm, &pl);
-        size_t dyn = (size_t)pl.total * sizeof(double);
         int occ = h->opts.occupancy;  // 0 auto
         if (occ == 0) occ = many ? 4 : 1;
+        if (!h->opts.threads && many && threads > 256) threads = 256;
+        bool ipm = (phase == SQPQP_PHASE_FR ? P.has_chol_fr : P.has_chol) && h->opts.method != 1;
+        const CholDev& CD = (phase == SQPQP_PHASE_FR) ? P.chol_fr : P.chol;
+        size_t budget = occ >= 8 ? 24 * 1024 : (occ >= 4 ? (size_t)h->cta4_smem : (size_t)h->max_dyn_smem);
+        bool vectors = occ < 4;
+        if (h->opts.smem_kb >= 0) {  // explicit budget for the vectors (0 = none)
+            vectors = h->opts.smem_kb > 0;
+            if ((size_t)h->opts.smem_kb * 1024 < budget && vectors) budget = (size_t)h->opts.smem_kb * 1024;
+        }
+        Placement pl;
+        place_arrays(P, phase, budget, ipm, vectors, &pl);
+        if (ipm && CD.T > 0 && pl.dtail < 0 && occ >= 8) {  // the tail was sized for four CTAs per SM
+            occ = 4;
+            budget = (size_t)h->cta4_smem;
+            place_arrays(P, phase, budget, ipm, vectors, &pl);
+        }
+        if (ipm && CD.T > 0 && pl.dtail < 0) return fail(h, SQPQP_E_STATE, "dense tail of the factor does not fit the shared-memory budget of this launch configuration");
+        size_t dyn = (size_t)pl.total * sizeof(double);
         if (occ >= 8 && threads <= 128) k_solve_cta<128, 8><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
         else if (occ >= 4 && threads <= 256) k_solve_cta<256, 4><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
         else k_solve_cta<512, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);

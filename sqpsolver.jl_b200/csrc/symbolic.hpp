@@ -6,10 +6,17 @@
 // solve (only d, w and the values of P, J change).  Done once at setup, in plain C++:
 //   1. pattern of K = pattern(P) U pattern(J'J) U I
 //   2. fill-reducing ordering: minimum degree on the elimination graph (exact external degree)
-//   3. symbolic Cholesky: column structure of L (by-product of 2.), elimination-tree levels
-//   4. the three index programs the device kernels execute:
-//        assembly : K_e  = P[h_idx] + d[diag] + sum_t w[row_t] * Jv[a_t] * Jv[b_t]
-//        factor   : L_e  = (K_e - sum_t L[p_t] * L[q_t]) / L_jj       (level by level)
+//   3. elimination tree and its levels; the columns are then RENUMBERED LEVEL-MAJOR (any
+//      topological order of the elimination tree gives the same fill), so that
+//        * the columns of one level are a contiguous range -> no indirection through a level list,
+//        * the entries of L (CSC, diagonal first) are stored in execution order,
+//        * the top of the tree -- a chain of single-column levels, where the factor is nearly
+//          dense and a level-scheduled sparse code would pay one barrier and one dependent gather
+//          chain per column -- is the LAST T columns: the "dense tail".  Its Schur complement is
+//          formed in one parallel phase and factorised as a dense packed matrix in shared memory.
+//   4. the index programs the device kernels execute:
+//        assembly : K_e  = P[h] + d[diag] + sum_t w[row_t] * Jv[a_t] * Jv[b_t]
+//        factor   : L_e  = (K_e - sum_t L[p_t] * L[q_t]) / L_jj    over columns k < min(j, n0)
 //        solve    : level-scheduled forward (rows of L) and backward (columns of L) sweeps
 // No numerical work happens here.
 #pragma once
@@ -18,29 +25,30 @@
 #include <vector>
 
 struct Symbolic {
-    int n = 0, nnzL = 0, nlev = 0;
+    int n = 0, nnzL = 0;
+    int nlev = 0;                        // number of SPARSE levels (columns 0 .. n0-1)
+    int n0 = 0, T = 0;                   // dense tail = columns n0 .. n-1 (T = n - n0; 0 = none)
+    int nlev_total = 0;                  // levels of the whole elimination tree (statistics)
     std::vector<int> perm, iperm;        // perm[k] = original index of pivot k
     std::vector<int> Lp, Li;             // CSC of L (permuted indices), diagonal first in each column
-    std::vector<int> Rp, Rc, Ri;         // CSR of strictly-lower L: row ptr, column, index into the CSC value array
-    std::vector<int> lev_ptr, lev_cols;  // columns grouped by elimination-tree level (leaves first)
-    // factorisation program: entries ordered by (level, diagonal-before-offdiagonal)
-    std::vector<int> fd_ptr, fo_ptr;     // per level: range in f_ent of diagonal / off-diagonal entries
-    std::vector<int> f_ent;              // entry ids (index into L values)
-    std::vector<int> fp_ptr;             // per entry id: range in fp_a/fp_b
-    std::vector<int> fp_a, fp_b;         // pairs of L value indices to multiply-subtract
-    std::vector<int> ent_diag;           // per entry id: value index of the diagonal of its column
+    std::vector<int> Rp, Rmid;           // CSR of strictly-lower L: row ptr; Rmid[j] = end of the part with column < n0
+    std::vector<int> Rci;                // interleaved (index into the CSC value array, column) per CSR entry
+    std::vector<int> lev_ptr;            // [nlev+1] column range of each sparse level
+    std::vector<int> fp_ptr;             // per entry id: range in fp_ab
+    std::vector<int> fp_ab;              // interleaved pairs of L value indices to multiply-subtract
+    std::vector<int> tpos;               // per tail entry (id - Lp[n0]): position in the packed dense tail
     // assembly program
-    std::vector<int> as_ptr;             // per entry id: range in as_a/as_b/as_r
-    std::vector<int> as_a, as_b, as_r;   // Jv index a, Jv index b, row (weight index)
-    std::vector<int> as_h;               // per entry id: index into P values or -1
-    std::vector<int> as_d;               // per entry id: original column for d[] (diagonal entries) or -1
-    int64_t flops = 0;
+    std::vector<int> as_hd;              // per entry id, interleaved (P value index or -1, original column for d[] or -1,
+                                         //                            begin, end of its terms in as_abr)
+    std::vector<int> as_abr;             // per term, interleaved (Jv index a, Jv index b, row = weight index, 0)
+    int64_t flops = 0;                   // of the sparse part (2 * pairs)
     bool ok = false;                     // false: a row of J is too long for the clique expansion
 };
 
-// J: m x ncols CSR (rb/re per row, so a prefix of each row can be used), P: symmetric-full CSR or null
+// J: m x ncols CSR (rb/re per row, so a prefix of each row can be used), P: symmetric-full CSR or null.
+// tail_max: largest dense tail (columns) the caller can hold; 0 disables the dense tail.
 inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, const int* Jcol, const int* Prp,
-                                 const int* Pcol, int max_row_len = 512) {
+                                 const int* Pcol, int max_row_len = 512, int tail_max = 0) {
     Symbolic S;
     S.n = n;
     // ---- 1. adjacency of K ---------------------------------------------------------------
@@ -58,7 +66,7 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
                 if (Pcol[k] != j) { adj[j].push_back(Pcol[k]); adj[Pcol[k]].push_back(j); }
     for (auto& v : adj) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
 
-    // ---- 2./3. minimum degree elimination; column structures fall out ----------------------
+    // ---- 2. minimum degree elimination; column structures fall out ---------------------------
     std::vector<char> done(n, 0);
     std::vector<int> order;
     order.reserve(n);
@@ -83,6 +91,41 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
         adj[v].clear();
         adj[v].shrink_to_fit();
     }
+    // ---- 3. elimination tree, levels, level-major renumbering, dense tail ---------------------
+    {
+        std::vector<int> ip0(n), parent(n, -1), level(n, 0);
+        for (int k = 0; k < n; ++k) ip0[order[k]] = k;
+        for (int k = 0; k < n; ++k) {
+            int p = n;
+            for (int u : colstruct[k]) p = std::min(p, ip0[u]);
+            parent[k] = p < n ? p : -1;
+        }
+        for (int k = 0; k < n; ++k)  // parent[k] > k: one ascending pass settles every level
+            if (parent[k] >= 0) level[parent[k]] = std::max(level[parent[k]], level[k] + 1);
+        int nl = 0;
+        for (int k = 0; k < n; ++k) nl = std::max(nl, level[k] + 1);
+        S.nlev_total = nl;
+        std::vector<int> pos(n);
+        for (int k = 0; k < n; ++k) pos[k] = k;
+        std::stable_sort(pos.begin(), pos.end(), [&](int a, int b) { return level[a] < level[b]; });
+        std::vector<int> cnt(nl + 1, 0);
+        for (int k = 0; k < n; ++k) cnt[level[k] + 1]++;
+        for (int l = 0; l < nl; ++l) cnt[l + 1] += cnt[l];
+        // dense tail: the top levels, as many as fit tail_max columns
+        int lcut = nl;
+        while (lcut > 0 && n - cnt[lcut - 1] <= tail_max) --lcut;
+        int T = n - cnt[lcut];
+        if (T < 16 || lcut == 0) { lcut = nl; T = 0; }  // not worth it / everything dense (tiny problems): plain sparse code
+        S.T = T;
+        S.n0 = n - T;
+        S.nlev = lcut;
+        S.lev_ptr.assign(cnt.begin(), cnt.begin() + lcut + 1);
+        std::vector<int> order2(n);
+        std::vector<std::vector<int>> cs2(n);
+        for (int k = 0; k < n; ++k) { order2[k] = order[pos[k]]; cs2[k].swap(colstruct[pos[k]]); }
+        order.swap(order2);
+        colstruct.swap(cs2);
+    }
     S.perm = order;
     S.iperm.assign(n, 0);
     for (int k = 0; k < n; ++k) S.iperm[order[k]] = k;
@@ -99,87 +142,72 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
         std::sort(rows.begin(), rows.end());
         for (int r : rows) S.Li[p++] = r;
     }
-    // elimination tree + levels
-    std::vector<int> parent(n, -1), level(n, 0);
-    for (int k = 0; k < n; ++k)
-        if (S.Lp[k + 1] - S.Lp[k] > 1) parent[k] = S.Li[S.Lp[k] + 1];
-    for (int k = 0; k < n; ++k)
-        if (parent[k] >= 0) level[parent[k]] = std::max(level[parent[k]], level[k] + 1);
-    S.nlev = 0;
-    for (int k = 0; k < n; ++k) S.nlev = std::max(S.nlev, level[k] + 1);
-    S.lev_ptr.assign(S.nlev + 1, 0);
-    for (int k = 0; k < n; ++k) S.lev_ptr[level[k] + 1]++;
-    for (int l = 0; l < S.nlev; ++l) S.lev_ptr[l + 1] += S.lev_ptr[l];
-    S.lev_cols.resize(n);
-    {
-        std::vector<int> cur(S.lev_ptr.begin(), S.lev_ptr.end() - 1);
-        for (int k = 0; k < n; ++k) S.lev_cols[cur[level[k]]++] = k;
-    }
-    // CSR of strictly-lower L (row i: columns k < i)
+    // CSR of strictly-lower L (row i: columns k < i, ascending)
+    const int n0 = S.n0;
+    std::vector<int> Rc, Ri;
     S.Rp.assign(n + 1, 0);
     for (int k = 0; k < n; ++k)
         for (int p = S.Lp[k] + 1; p < S.Lp[k + 1]; ++p) S.Rp[S.Li[p] + 1]++;
     for (int i = 0; i < n; ++i) S.Rp[i + 1] += S.Rp[i];
-    S.Rc.resize(S.Rp[n]);
-    S.Ri.resize(S.Rp[n]);
+    Rc.resize(S.Rp[n]);
+    Ri.resize(S.Rp[n]);
     {
         std::vector<int> cur(S.Rp.begin(), S.Rp.end() - 1);
         for (int k = 0; k < n; ++k)
             for (int p = S.Lp[k] + 1; p < S.Lp[k + 1]; ++p) {
                 int i = S.Li[p];
-                S.Rc[cur[i]] = k;
-                S.Ri[cur[i]++] = p;
+                Rc[cur[i]] = k;
+                Ri[cur[i]++] = p;
             }
     }
+    S.Rmid.resize(n);
+    S.Rci.resize(2 * (size_t)S.Rp[n]);
+    for (int i = 0; i < n; ++i) {
+        int q = S.Rp[i];
+        while (q < S.Rp[i + 1] && Rc[q] < n0) ++q;
+        S.Rmid[i] = q;
+    }
+    for (int q = 0; q < S.Rp[n]; ++q) { S.Rci[2 * q] = Ri[q]; S.Rci[2 * q + 1] = Rc[q]; }
     // ---- 4a. factorisation program ------------------------------------------------------------
-    // entry (i,j), j<=i:  sum over k<j with L_ik != 0 and L_jk != 0 -> intersect rows i and j of the CSR
+    // entry (i,j), j<=i:  sum over k < min(j, n0) with L_ik != 0 and L_jk != 0 -> intersect rows i and j of the CSR
     S.fp_ptr.assign(S.nnzL + 1, 0);
-    S.ent_diag.resize(S.nnzL);
     for (int pass = 0; pass < 2; ++pass) {
         int64_t total = 0;
-        for (int j = 0; j < n; ++j)
+        for (int j = 0; j < n; ++j) {
+            const int lim = std::min(j, n0);
             for (int p = S.Lp[j]; p < S.Lp[j + 1]; ++p) {
                 int i = S.Li[p];
-                S.ent_diag[p] = S.Lp[j];
                 int a = S.Rp[i], ae = S.Rp[i + 1], b = S.Rp[j], be = S.Rp[j + 1];
                 int cnt = 0;
                 while (a < ae && b < be) {
-                    int ca = S.Rc[a], cb = S.Rc[b];
-                    if (ca >= j || cb >= j) break;
+                    int ca = Rc[a], cb = Rc[b];
+                    if (ca >= lim || cb >= lim) break;
                     if (ca == cb) {
-                        if (pass) { S.fp_a[S.fp_ptr[p] + cnt] = S.Ri[a]; S.fp_b[S.fp_ptr[p] + cnt] = S.Ri[b]; }
+                        if (pass) { S.fp_ab[2 * (size_t)(S.fp_ptr[p] + cnt)] = Ri[a]; S.fp_ab[2 * (size_t)(S.fp_ptr[p] + cnt) + 1] = Ri[b]; }
                         ++cnt; ++a; ++b;
                     } else if (ca < cb) ++a; else ++b;
                 }
                 if (!pass) S.fp_ptr[p + 1] = cnt;
                 total += cnt;
             }
+        }
         if (!pass) {
             for (int p = 0; p < S.nnzL; ++p) S.fp_ptr[p + 1] += S.fp_ptr[p];
-            S.fp_a.resize(S.fp_ptr[S.nnzL]);
-            S.fp_b.resize(S.fp_ptr[S.nnzL]);
+            S.fp_ab.resize(2 * (size_t)S.fp_ptr[S.nnzL]);
             S.flops = 2 * total;
         }
     }
-    S.fd_ptr.assign(S.nlev + 1, 0);
-    S.fo_ptr.assign(S.nlev + 1, 0);
-    S.f_ent.clear();
-    // layout of f_ent: for each level: [diag entries][offdiag entries]
-    for (int l = 0; l < S.nlev; ++l) {
-        S.fd_ptr[l] = (int)S.f_ent.size();
-        for (int t = S.lev_ptr[l]; t < S.lev_ptr[l + 1]; ++t) S.f_ent.push_back(S.Lp[S.lev_cols[t]]);
-        S.fo_ptr[l] = (int)S.f_ent.size();
-        for (int t = S.lev_ptr[l]; t < S.lev_ptr[l + 1]; ++t) {
-            int j = S.lev_cols[t];
-            for (int p = S.Lp[j] + 1; p < S.Lp[j + 1]; ++p) S.f_ent.push_back(p);
+    // packed position (row-major lower triangle of the T x T tail) of every tail entry
+    S.tpos.clear();
+    for (int j = n0; j < n; ++j)
+        for (int p = S.Lp[j]; p < S.Lp[j + 1]; ++p) {
+            int r = S.Li[p] - n0, c = j - n0;
+            S.tpos.push_back(r * (r + 1) / 2 + c);
         }
-    }
-    S.fd_ptr[S.nlev] = S.fo_ptr[S.nlev] = (int)S.f_ent.size();
 
     // ---- 4b. assembly program --------------------------------------------------------------------
     // map (i,j) permuted, i>=j -> entry id
-    S.as_h.assign(S.nnzL, -1);
-    S.as_d.assign(S.nnzL, -1);
+    std::vector<int> as_h(S.nnzL, -1), as_d(S.nnzL, -1);
     auto find_entry = [&](int a, int b) {  // original indices
         int i = S.iperm[a], j = S.iperm[b];
         if (i < j) std::swap(i, j);
@@ -189,14 +217,14 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
         const int* it = std::lower_bound(lo, hi, i);
         return (int)(it - &S.Li[0]);
     };
-    for (int k = 0; k < n; ++k) S.as_d[S.Lp[k]] = S.perm[k];
+    for (int k = 0; k < n; ++k) as_d[S.Lp[k]] = S.perm[k];
     if (Prp)
         for (int a = 0; a < n; ++a)
             for (int k = Prp[a]; k < Prp[a + 1]; ++k) {
                 int b = Pcol[k];
-                if (S.iperm[a] >= S.iperm[b]) S.as_h[find_entry(a, b)] = k;  // lower triangle in permuted order
+                if (S.iperm[a] >= S.iperm[b]) as_h[find_entry(a, b)] = k;  // lower triangle in permuted order
             }
-    std::vector<int> cnt(S.nnzL + 1, 0);
+    std::vector<int> cnt(S.nnzL + 1, 0), as_ptr;
     for (int pass = 0; pass < 2; ++pass) {
         for (int r = 0; r < m; ++r)
             for (int a = Jrb[r]; a < Jre[r]; ++a)
@@ -207,18 +235,21 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
                     int e = find_entry(ca, cb);
                     if (!pass) cnt[e + 1]++;
                     else {
-                        int pos = S.as_ptr[e] + cnt[e]++;
-                        S.as_a[pos] = a; S.as_b[pos] = b; S.as_r[pos] = r;
+                        size_t pos = (size_t)as_ptr[e] + cnt[e]++;
+                        S.as_abr[4 * pos] = a; S.as_abr[4 * pos + 1] = b; S.as_abr[4 * pos + 2] = r; S.as_abr[4 * pos + 3] = 0;
                     }
                 }
         if (!pass) {
-            S.as_ptr.assign(S.nnzL + 1, 0);
-            for (int e = 0; e < S.nnzL; ++e) S.as_ptr[e + 1] = S.as_ptr[e] + cnt[e + 1];
-            S.as_a.resize(S.as_ptr[S.nnzL]);
-            S.as_b.resize(S.as_ptr[S.nnzL]);
-            S.as_r.resize(S.as_ptr[S.nnzL]);
+            as_ptr.assign(S.nnzL + 1, 0);
+            for (int e = 0; e < S.nnzL; ++e) as_ptr[e + 1] = as_ptr[e] + cnt[e + 1];
+            S.as_abr.resize(4 * (size_t)as_ptr[S.nnzL]);
             std::fill(cnt.begin(), cnt.end(), 0);
         }
+    }
+    S.as_hd.resize(4 * (size_t)S.nnzL);
+    for (int e = 0; e < S.nnzL; ++e) {
+        S.as_hd[4 * (size_t)e] = as_h[e]; S.as_hd[4 * (size_t)e + 1] = as_d[e];
+        S.as_hd[4 * (size_t)e + 2] = as_ptr[e]; S.as_hd[4 * (size_t)e + 3] = as_ptr[e + 1];
     }
     S.ok = true;
     return S;
