@@ -356,6 +356,7 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
         W.L = fr ? P.Lval_fr + (size_t)inst * CD.nnzL : P.Lval + (size_t)inst * CD.nnzL;
         W.yw = fr ? P.yw_fr + (size_t)inst * P.Ne : P.yw + (size_t)inst * P.n;
         W.dinv = fr ? P.dinv_fr + (size_t)inst * P.Ne : P.dinv + (size_t)inst * P.n;
+        W.wJ = P.wJ + (size_t)inst * P.nnzJ;
         W.D = W.col = nullptr;
         if (pl) {  // shared-memory parts of the factorisation (the dense tail lives nowhere else)
             if (pl->lval >= 0) W.L = dsm + pl->lval;

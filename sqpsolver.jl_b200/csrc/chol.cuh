@@ -8,22 +8,21 @@
 // plus -- CTA teams -- the dense tail of the factor, the inverse diagonal and the solve scratch in
 // shared memory.
 //
-//   sparse levels (columns 0..n0-1): one barrier phase per elimination-tree level; a sub-warp owns
-//       a column, forms its diagonal cooperatively and then its sub-diagonal entries lane by lane.
-//       Entries are stored in execution order, so the only dependent chain per phase is
-//       column pointer -> pair list -> L values.
+//   sparse levels (columns 0..n0-1): two barrier phases per elimination-tree level (diagonal, then
+//       sub-diagonal entries), each a flat task list with one coalesced descriptor per task; a
+//       sub-warp per task, its multiply-subtract pairs gathered four chains at a time.  The
+//       dependent chain of a phase is descriptor -> pair list -> L values.
 //   dense tail (last T columns = the chain at the top of the tree, where L is nearly dense):
 //       its Schur complement is gathered in ONE parallel phase into a packed T x T lower triangle
-//       in shared memory and factorised there by a right-looking dense Cholesky (2 cheap
-//       shared-memory barriers per column, no global traffic); the triangular solves on it run in
-//       registers of one warp with shuffle broadcasts.
+//       in shared memory and factorised there by a left-looking dense Cholesky (one shared-memory
+//       barrier per column, no global traffic); the triangular solves on it run in registers of
+//       one warp with shuffle broadcasts.
 // Deterministic (no atomics); a non-positive pivot is reported, never hidden.
 #pragma once
 #include "team.cuh"
 
-// lanes (power of two <= 32) that cooperate on one column/row of a level with `count`
-// independent items: wide when the level is narrow, 1 when the level has at least as many items
-// as the team has threads.
+// lanes (power of two <= 32) that cooperate on one task of a phase with `count` independent
+// tasks: wide when the phase is narrow, 1 when it has at least as many tasks as the team has threads.
 template <class Team>
 __device__ __forceinline__ int level_lg(Team& T, int count) {
     int lg = 0;
@@ -35,25 +34,83 @@ __device__ __forceinline__ double subwarp_sum(double v, int L) {
     return v;
 }
 
-// L <- lower triangle of K in the permuted order (all entries, tail included).  Pv may be null
-// (no P); dg[j] is added to the diagonal entry of ORIGINAL column j.  Also clears the dense tail.
+// sum_{q = q0, q0 + step, ... < qe} A[ab[q].x] * B[ab[q].y] with four independent gather chains in
+// flight (index -> value is a dependent L2 round trip; a plain loop would pay it once per pair).
+__device__ __forceinline__ double gather_dot(const int2* __restrict__ ab, int q, const int qe, const int step,
+                                             const double* A, const double* B) {
+    double acc0 = 0.0, acc1 = 0.0;
+    for (; q + 3 * step < qe; q += 4 * step) {
+        const int2 p0 = ab[q], p1 = ab[q + step], p2 = ab[q + 2 * step], p3 = ab[q + 3 * step];
+        const double a0 = A[p0.x], b0 = B[p0.y], a1 = A[p1.x], b1 = B[p1.y];
+        const double a2 = A[p2.x], b2 = B[p2.y], a3 = A[p3.x], b3 = B[p3.y];
+        acc0 = fma(a0, b0, acc0); acc1 = fma(a1, b1, acc1);
+        acc0 = fma(a2, b2, acc0); acc1 = fma(a3, b3, acc1);
+    }
+    if (q < qe) {
+        const bool h1 = q + step < qe, h2 = q + 2 * step < qe;
+        const int2 p0 = ab[q], p1 = h1 ? ab[q + step] : p0, p2 = h2 ? ab[q + 2 * step] : p0;
+        const double a0 = A[p0.x], b0 = B[p0.y], a1 = A[p1.x], b1 = B[p1.y], a2 = A[p2.x], b2 = B[p2.y];
+        acc0 = fma(a0, b0, acc0);
+        if (h1) acc1 = fma(a1, b1, acc1);
+        if (h2) acc0 = fma(a2, b2, acc0);
+    }
+    return acc0 + acc1;
+}
+// sum_{p = p0, p0 + step, ... < pe} V[p] * Y[idx[p]]  (a column of L against the solve scratch)
+__device__ __forceinline__ double column_dot(const double* __restrict__ V, const int* __restrict__ idx, int p, const int pe,
+                                             const int step, const double* Y) {
+    double acc0 = 0.0, acc1 = 0.0;
+    for (; p + 3 * step < pe; p += 4 * step) {
+        const int i0 = idx[p], i1 = idx[p + step], i2 = idx[p + 2 * step], i3 = idx[p + 3 * step];
+        const double v0 = V[p], v1 = V[p + step], v2 = V[p + 2 * step], v3 = V[p + 3 * step];
+        acc0 = fma(v0, Y[i0], acc0); acc1 = fma(v1, Y[i1], acc1);
+        acc0 = fma(v2, Y[i2], acc0); acc1 = fma(v3, Y[i3], acc1);
+    }
+    for (; p < pe; p += step) acc0 = fma(V[p], Y[idx[p]], acc0);
+    return acc0 + acc1;
+}
+
+// L <- lower triangle of K in the permuted order, sourced entries only (pure fill entries have
+// K_e = 0 and are never read: their factor task carries has_K = 0).  Pv may be null (no P); dg[j] is
+// added to the diagonal entry of ORIGINAL column j.  Also clears the dense tail.
 template <class Team>
 __device__ void chol_assemble(Team& T, const CholDev& C, const CholWork& W, const double* __restrict__ Pv,
                               const double* __restrict__ dg, const double* __restrict__ w, const double* __restrict__ Jv) {
     double* __restrict__ L = W.L;
-    for (int e = T.tid(); e < C.nnzL; e += T.size()) {
-        const int4 hd = C.as_hd[e];
-        double v = 0.0;
-        if (Pv && hd.x >= 0) v += Pv[hd.x];
-        if (hd.y >= 0) v += dg[hd.y];
-        for (int t = hd.z; t < hd.w; ++t) {
-            const int4 abr = C.as_abr[t];
-            v = fma(w[abr.z] * Jv[abr.x], Jv[abr.y], v);
-        }
-        L[e] = v;
+    double* __restrict__ wJ = W.wJ;
+    for (int a = T.tid(); a < C.nslotJ; a += T.size()) {
+        const int r = C.jrow[a];
+        wJ[a] = r >= 0 ? w[r] * Jv[a] : 0.0;
     }
     if (C.T > 0)
         for (int i = T.tid(); i < C.T * (C.T + 1) / 2; i += T.size()) W.D[i] = 0.0;
+    T.sync();
+    // two tasks per thread and round, their (short) term lists walked together so that both gather
+    // chains are in flight
+    const int nt = C.n + C.n_aoff, stride = T.size();
+    const int2* __restrict__ ab = C.as_ab;
+    for (int t = T.tid(); t < nt; t += 2 * stride) {
+        const int t2 = t + stride;
+        const bool has2 = t2 < nt;
+        const int4 k1 = t < C.n ? C.atask_diag[t] : C.atask_off[t - C.n];
+        const int4 k2 = has2 ? (t2 < C.n ? C.atask_diag[t2] : C.atask_off[t2 - C.n]) : make_int4(0, 0, 0, -1);
+        double v1 = (Pv && k1.w >= 0) ? Pv[k1.w] : 0.0;
+        double v2 = (Pv && k2.w >= 0) ? Pv[k2.w] : 0.0;
+        if (t < C.n) v1 += dg[C.perm[t]];
+        if (has2 && t2 < C.n) v2 += dg[C.perm[t2]];
+        int q1 = k1.y, q2 = k2.y;
+        const int e1 = k1.z, e2 = k2.z;
+        while (q1 < e1 || q2 < e2) {
+            const bool o1 = q1 < e1, o2 = q2 < e2;
+            const int2 p1 = ab[o1 ? q1 : 0], p2 = ab[o2 ? q2 : 0];
+            const double a1 = wJ[p1.x], b1 = Jv[p1.y], a2 = wJ[p2.x], b2 = Jv[p2.y];
+            if (o1) v1 = fma(a1, b1, v1);
+            if (o2) v2 = fma(a2, b2, v2);
+            ++q1; ++q2;
+        }
+        L[k1.x] = v1;
+        if (has2) L[k2.x] = v2;
+    }
     T.sync();
 }
 
@@ -61,26 +118,44 @@ __device__ void chol_assemble(Team& T, const CholDev& C, const CholWork& W, cons
 // packed row-major lower triangle: (r, c), c <= r, at r (r + 1) / 2 + c
 __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 
-// right-looking dense Cholesky of D (T x T); writes 1/L_jj to dinvT[0..T).  Returns 1.0 if a pivot
-// was not positive (every thread sees the same pivots, so the flag is uniform).
-__device__ inline double dense_factor(double* __restrict__ D, double* __restrict__ col, double* __restrict__ dinvT, int Tn) {
-    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wp = tid >> 5, nw = nth >> 5;
+// Left-looking dense Cholesky of the packed D (T x T): in step j a sub-warp per remaining row i >= j
+// forms  S_ij - sum_{k<j} L_ik L_jk  and -- redundantly, it streams row j anyway --  the pivot
+// S_jj - sum_{k<j} L_jk^2, so one barrier per column suffices.  The lanes per row grow as the rows
+// run out (the dots get longer as the rows get fewer).  D[j][j] keeps S_jj; 1/L_jj goes to dinvT.
+// Returns 1.0 if a pivot was not positive (uniform: every sub-warp sees the same pivots).
+__device__ inline double dense_factor(double* __restrict__ D, double* __restrict__ dinvT, int Tn) {
+    const int tid = threadIdx.x, nth = blockDim.x;
     double bad = 0.0;
     for (int j = 0; j < Tn; ++j) {
-        double d = D[tri(j) + j];
-        if (!(d > 0.0)) { bad = 1.0; d = 1.0; }
-        const double inv = 1.0 / sqrt(d);
-        for (int i = j + 1 + tid; i < Tn; i += nth) {
-            double c = D[tri(i) + j] * inv;
-            D[tri(i) + j] = c;
-            col[i] = c;
-        }
-        if (tid == 0) dinvT[j] = inv;
-        __syncthreads();
-        for (int i = j + 1 + wp; i < Tn; i += nw) {
-            const double ci = col[i];
-            double* __restrict__ row = D + tri(i);
-            for (int k = j + 1 + lane; k <= i; k += 32) row[k] = fma(-ci, col[k], row[k]);
+        const int rows = Tn - j;
+        int lg = 0;
+        while (lg < 5 && (rows << (lg + 1)) <= nth) ++lg;
+        const int G = 1 << lg, lane = tid & (G - 1), sub = tid >> lg, nsub = nth >> lg;
+        const double* __restrict__ rowj = D + tri(j);
+        for (int i0 = j; i0 < Tn; i0 += nsub) {
+            const int i = i0 + sub;
+            const bool on = i < Tn;
+            double* __restrict__ rowi = D + tri(on ? i : j);
+            double di0 = 0.0, di1 = 0.0, dj0 = 0.0, dj1 = 0.0;
+            int k = lane;
+            for (; k + G < j; k += 2 * G) {
+                const double a0 = rowj[k], a1 = rowj[k + G], b0 = rowi[k], b1 = rowi[k + G];
+                di0 = fma(b0, a0, di0); dj0 = fma(a0, a0, dj0);
+                di1 = fma(b1, a1, di1); dj1 = fma(a1, a1, dj1);
+            }
+            if (k < j) { const double a0 = rowj[k]; di0 = fma(rowi[k], a0, di0); dj0 = fma(a0, a0, dj0); }
+            double di = di0 + di1, dj = dj0 + dj1;
+            for (int o = G >> 1; o > 0; o >>= 1) {
+                di += __shfl_xor_sync(0xffffffffu, di, o);
+                dj += __shfl_xor_sync(0xffffffffu, dj, o);
+            }
+            double pv = rowj[j] - dj;
+            if (!(pv > 0.0)) { bad = 1.0; pv = 1.0; }
+            const double inv = rsqrt(pv);
+            if (on && lane == 0) {
+                if (i == j) dinvT[j] = inv;
+                else rowi[j] = (rowi[j] - di) * inv;
+            }
         }
         __syncthreads();
     }
@@ -88,8 +163,8 @@ __device__ inline double dense_factor(double* __restrict__ D, double* __restrict
 }
 
 // y <- L_T^{-1} y, then y <- L_T^{-T} y on the tail part of the solve scratch; one warp, the
-// right-hand side in registers (lane owns rows lane, lane+32, ...), pivots broadcast by shuffle.
-// Tn <= 128.
+// right-hand side in registers (lane owns rows lane, lane+32, ...), pivots broadcast by shuffle:
+// the dependent chain of a step is shuffle -> multiply -> fma.  Tn <= 128.
 __device__ inline void dense_solve_warp(const double* __restrict__ D, const double* __restrict__ dinvT, double* yt, int Tn) {
     const int lane = threadIdx.x & 31;
     double t[4];
@@ -98,35 +173,43 @@ __device__ inline void dense_solve_warp(const double* __restrict__ D, const doub
     // forward, column oriented: y_j = t_j / L_jj ; t_i -= L_ij y_j  (i > j)
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-        if (32 * s >= Tn) break;
-        for (int jj = 0; jj < 32; ++jj) {
-            const int j = 32 * s + jj;
-            if (j >= Tn) break;
-            const double yj = __shfl_sync(0xffffffffu, t[s], jj) * dinvT[j];
-            if (lane == jj) t[s] = yj;
+        if (32 * s < Tn) {
+            const int jend = (Tn - 32 * s) < 32 ? (Tn - 32 * s) : 32;
+            for (int jj = 0; jj < jend; ++jj) {
+                const int j = 32 * s + jj;
+                double dl[4];
 #pragma unroll
-            for (int s2 = 0; s2 < 4; ++s2) {
-                if (s2 < s) continue;
-                const int i = lane + 32 * s2;
-                if (i > j && i < Tn) t[s2] = fma(-D[tri(i) + j], yj, t[s2]);
+                for (int s2 = 0; s2 < 4; ++s2) {
+                    const int i = lane + 32 * s2;
+                    dl[s2] = (s2 >= s && i > j && i < Tn) ? D[tri(i) + j] : 0.0;
+                }
+                const double yj = __shfl_sync(0xffffffffu, t[s], jj) * dinvT[j];
+                if (lane == jj) t[s] = yj;
+#pragma unroll
+                for (int s2 = 0; s2 < 4; ++s2)
+                    if (s2 >= s) t[s2] = fma(-dl[s2], yj, t[s2]);
             }
         }
     }
     // backward, row oriented on L' : x_j = t_j / L_jj ; t_k -= L_jk x_j  (k < j)
 #pragma unroll
     for (int s = 3; s >= 0; --s) {
-        if (32 * s >= Tn) continue;
-        for (int jj = 31; jj >= 0; --jj) {
-            const int j = 32 * s + jj;
-            if (j >= Tn) continue;
-            const double xj = __shfl_sync(0xffffffffu, t[s], jj) * dinvT[j];
-            if (lane == jj) t[s] = xj;
-            const double* __restrict__ row = D + tri(j);
+        if (32 * s < Tn) {
+            const int jend = (Tn - 32 * s) < 32 ? (Tn - 32 * s) : 32;
+            for (int jj = jend - 1; jj >= 0; --jj) {
+                const int j = 32 * s + jj;
+                const double* __restrict__ row = D + tri(j);
+                double dl[4];
 #pragma unroll
-            for (int s2 = 0; s2 < 4; ++s2) {
-                if (s2 > s) continue;
-                const int k = lane + 32 * s2;
-                if (k < j) t[s2] = fma(-row[k], xj, t[s2]);
+                for (int s2 = 0; s2 < 4; ++s2) {
+                    const int k = lane + 32 * s2;
+                    dl[s2] = (s2 <= s && k < j) ? row[k] : 0.0;
+                }
+                const double xj = __shfl_sync(0xffffffffu, t[s], jj) * dinvT[j];
+                if (lane == jj) t[s] = xj;
+#pragma unroll
+                for (int s2 = 0; s2 < 4; ++s2)
+                    if (s2 <= s) t[s2] = fma(-dl[s2], xj, t[s2]);
             }
         }
     }
@@ -135,65 +218,48 @@ __device__ inline void dense_solve_warp(const double* __restrict__ D, const doub
         if (lane + 32 * s < Tn) yt[lane + 32 * s] = t[s];
 }
 
-// In-place numeric factorisation.  Returns false (uniformly) if a pivot was not positive.
+// In-place numeric factorisation: the barrier phases of symbolic.hpp 4c (per sparse level the
+// diagonal entries, then the sub-diagonal entries; then the Schur complement of the dense tail), a
+// sub-warp per task.  Returns false (uniformly) if a pivot was not positive.
 template <class Team>
 __device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& pf) {
-    double* __restrict__ L = W.L;
+    double* L = W.L;
     double bad[1] = {0.0};
-    for (int l = 0; l < C.nlev; ++l) {
-        const int c0 = C.lev_ptr[l], cnt = C.lev_ptr[l + 1] - c0, lg = level_lg(T, cnt), Ln = 1 << lg;
+    int4 ph = C.fphase[0];
+    for (int p = 0; p < C.nphase; ++p) {
+        const int4 nxt = C.fphase[p + 1];  // (padded by one entry) off the critical path of the next phase
+        const int t0 = ph.x, nt = ph.y - ph.x, kind = ph.w;
+        const int lg = level_lg(T, nt), Ln = 1 << lg;
         const int lane = T.tid() & (Ln - 1), sub = T.tid() >> lg, nsub = T.size() >> lg;
-        for (int t0 = 0; t0 < cnt; t0 += nsub) {
-            const int t = t0 + sub;
-            const bool on = t < cnt;
-            const int j = c0 + (on ? t : 0);
-            const int e0 = C.Lp[j], e1 = on ? C.Lp[j + 1] : e0;
-            // diagonal: K_jj - sum_k L_jk^2, pairs spread over the sub-warp
-            double acc = 0.0;
-            if (on)
-                for (int q = C.fp_ptr[e0] + lane, qe = C.fp_ptr[e0 + 1]; q < qe; q += Ln) {
-                    double a = L[C.fp_ab[q].x];
-                    acc = fma(a, a, acc);
-                }
+        for (int r0 = 0; r0 < nt; r0 += nsub) {
+            const int t = r0 + sub;
+            const bool on = t < nt;
+            const int4 tk = C.ftask[t0 + (on ? t : 0)];
+            const int e = tk.x & 0x3fffffff;
+            const double k0 = (on && (tk.x >> 30)) ? L[e] : 0.0;
+            const double di = (on && kind == 1) ? W.dinv[tk.w] : 0.0;
+            double acc = on ? gather_dot(C.fp_ab, tk.y + lane, tk.z, Ln, L, L) : 0.0;
             acc = subwarp_sum(acc, Ln);
-            double d = L[e0] - acc;
-            if (on && !(d > 0.0)) { bad[0] = 1.0; d = 1.0; }
-            const double inv = on ? 1.0 / sqrt(d) : 0.0;
-            // sub-diagonal entries of the column, one lane each
-            for (int e = e0 + 1 + lane; e < e1; e += Ln) {
-                double a2 = 0.0;
-                for (int q = C.fp_ptr[e], qe = C.fp_ptr[e + 1]; q < qe; ++q) {
-                    const int2 ab = C.fp_ab[q];
-                    a2 = fma(L[ab.x], L[ab.y], a2);
+            if (on && lane == 0) {
+                double v = k0 - acc;
+                if (kind == 0) {
+                    if (!(v > 0.0)) { bad[0] = 1.0; v = 1.0; }
+                    const double inv = rsqrt(v);
+                    L[e] = v * inv;
+                    W.dinv[tk.w] = inv;
+                } else if (kind == 1) {
+                    L[e] = v * di;
+                } else {
+                    W.D[tk.w] = v;
                 }
-                L[e] = (L[e] - a2) * inv;
             }
-            __syncwarp();  // every lane has read K_jj before it is overwritten
-            if (on && lane == 0) { L[e0] = d * inv; W.dinv[j] = inv; }
         }
         T.sync();
+        ph = nxt;
     }
     pf.lap(PS_FACTOR_SPARSE);
     if (C.T > 0) {
-        // Schur complement of the tail: S_ij = K_ij - sum_{k < n0} L_ik L_jk, all entries independent
-        const int base = C.Lp[C.n0], ne = C.nnzL - base, lg = level_lg(T, ne), Ln = 1 << lg;
-        const int lane = T.tid() & (Ln - 1), sub = T.tid() >> lg, nsub = T.size() >> lg;
-        for (int t0 = 0; t0 < ne; t0 += nsub) {
-            const int t = t0 + sub;
-            const bool on = t < ne;
-            const int e = base + (on ? t : 0);
-            double acc = 0.0;
-            if (on)
-                for (int q = C.fp_ptr[e] + lane, qe = C.fp_ptr[e + 1]; q < qe; q += Ln) {
-                    const int2 ab = C.fp_ab[q];
-                    acc = fma(L[ab.x], L[ab.y], acc);
-                }
-            acc = subwarp_sum(acc, Ln);
-            if (on && lane == 0) W.D[C.tpos[t]] = L[e] - acc;
-        }
-        T.sync();
-        pf.lap(PS_SCHUR);
-        bad[0] = fmax(bad[0], dense_factor(W.D, W.col, W.dinv + C.n0, C.T));
+        bad[0] = fmax(bad[0], dense_factor(W.D, W.dinv + C.n0, C.T));
         pf.lap(PS_FACTOR_DENSE);
     }
     T.template reduce<1, true>(bad);
@@ -203,9 +269,9 @@ __device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& 
 // x = K^{-1} b   (b, x in original order; x may alias b)
 template <class Team>
 __device__ void chol_solve(Team& T, const CholDev& C, const CholWork& W, const double* b, double* x, Prof& pf) {
-    const double* __restrict__ L = W.L;
+    const double* L = W.L;
     double* yw = W.yw;
-    const double* __restrict__ dinv = W.dinv;
+    const double* dinv = W.dinv;
     for (int k = T.tid(); k < C.n; k += T.size()) yw[k] = b[C.perm[k]];
     T.sync();
     for (int l = 0; l < C.nlev; ++l) {  // forward: rows of L
@@ -215,14 +281,10 @@ __device__ void chol_solve(Team& T, const CholDev& C, const CholWork& W, const d
             const int t = t0 + sub;
             const bool on = t < cnt;
             const int j = c0 + (on ? t : 0);
-            double acc = 0.0;
-            if (on)
-                for (int q = C.Rp[j] + lane, qe = C.Rp[j + 1]; q < qe; q += Ln) {
-                    const int2 ic = C.Rci[q];
-                    acc = fma(L[ic.x], yw[ic.y], acc);
-                }
+            const double yj = yw[j], dj = dinv[j];
+            double acc = on ? gather_dot(C.Rci, C.Rp[j] + lane, C.Rp[j + 1], Ln, L, yw) : 0.0;
             acc = subwarp_sum(acc, Ln);
-            if (on && lane == 0) yw[j] = (yw[j] - acc) * dinv[j];
+            if (on && lane == 0) yw[j] = (yj - acc) * dj;
         }
         T.sync();
     }
@@ -235,12 +297,7 @@ __device__ void chol_solve(Team& T, const CholDev& C, const CholWork& W, const d
             const int t = t0 + sub;
             const bool on = t < C.T;
             const int j = C.n0 + (on ? t : 0);
-            double acc = 0.0;
-            if (on)
-                for (int q = C.Rp[j] + lane, qe = C.Rmid[j]; q < qe; q += Ln) {
-                    const int2 ic = C.Rci[q];
-                    acc = fma(L[ic.x], yw[ic.y], acc);
-                }
+            double acc = on ? gather_dot(C.Rci, C.Rp[j] + lane, C.Rmid[j], Ln, L, yw) : 0.0;
             acc = subwarp_sum(acc, Ln);
             if (on && lane == 0) yw[j] -= acc;
         }
@@ -256,11 +313,10 @@ __device__ void chol_solve(Team& T, const CholDev& C, const CholWork& W, const d
             const int t = t0 + sub;
             const bool on = t < cnt;
             const int j = c0 + (on ? t : 0);
-            double acc = 0.0;
-            if (on)
-                for (int p = C.Lp[j] + 1 + lane, pe = C.Lp[j + 1]; p < pe; p += Ln) acc = fma(L[p], yw[C.Li[p]], acc);
+            const double yj = yw[j], dj = dinv[j];
+            double acc = on ? column_dot(L, C.Li, C.Lp[j] + 1 + lane, C.Lp[j + 1], Ln, yw) : 0.0;
             acc = subwarp_sum(acc, Ln);
-            if (on && lane == 0) yw[j] = (yw[j] - acc) * dinv[j];
+            if (on && lane == 0) yw[j] = (yj - acc) * dj;
         }
         T.sync();
     }

@@ -41,16 +41,19 @@ struct Csr {
 // dense tail n0 .. n-1 (T columns, factorised as a packed dense matrix in shared memory).
 struct CholDev {
     int n, nnzL, nlev, n0, T;
+    int nphase, n_aoff, nslotJ;
     const int *perm;
     const int *Lp, *Li;
     const int *Rp, *Rmid;
-    const int2 *Rci;       // (value index, column) of the strictly-lower CSR
+    const int2 *Rci;        // (value index, column) of the strictly-lower CSR
     const int *lev_ptr;
-    const int *fp_ptr;
-    const int2 *fp_ab;     // pairs of value indices
-    const int *tpos;       // packed tail position of the tail entries
-    const int4 *as_hd;     // per entry: (P value index | -1, d index | -1, term begin, term end)
-    const int4 *as_abr;    // per term: (Jv a, Jv b, weight row, 0)
+    const int2 *fp_ab;      // pairs of value indices
+    const int4 *ftask;      // factorisation tasks  (entry | has_K << 30, first pair, end pair, aux)
+    const int4 *fphase;     // factorisation phases (first task, end task, max pairs, kind)
+    const int4 *atask_off;  // assembly of sourced sub-diagonal entries (entry, first term, end term, P index | -1)
+    const int4 *atask_diag; // assembly of the diagonal, one per column
+    const int2 *as_ab;      // assembly terms (wJ index, Jv index)
+    const int *jrow;        // row of every J value slot
 };
 
 // per-instance numeric state of the factorisation, resolved for one team
@@ -60,6 +63,7 @@ struct CholWork {
     double* col;    // [T] scaled pivot column of the dense factorisation (shared memory)
     double* dinv;   // [n] 1 / L_jj
     double* yw;     // [n] triangular-solve scratch in permuted order
+    double* wJ;     // [nslotJ] w[row] * Jv per J value slot (global)
 };
 
 struct Prob {
@@ -95,6 +99,7 @@ struct Prob {
     CholDev chol_fr;   // feasibility-restoration LP: n + S columns ([J|S]), P = 0
     int has_chol, has_chol_fr;
     double *Lval, *yw, *Lval_fr, *yw_fr;
+    double *wJ;               // [batch][nnzJ]
     double *dinv, *dinv_fr;   // [batch][n], [batch][Ne] (used when the shared-memory budget cannot hold them)
     // grid-team reduction scratch: [2][SQPQP_MAX_RED][maxblocks]
     double* gred;

@@ -52,6 +52,7 @@ struct sqpqp_handle_s {
     int num_sms = 148, coop_blocks = 0, max_dyn_smem = 0;
     int chol_nnzL = 0, chol_nlev = 0, chol_tail = 0, chol_nlev_total = 0;
     int cta4_smem = 48 * 1024;  // dynamic shared memory of one CTA when four share an SM
+    int cta2_smem = 100 * 1024; // ... when two share an SM (the default for large batches)
     int64_t chol_flops = 0;
     std::vector<double> avg_row;  // avg row length of J(normal), J(ext), T, H
     // generic-lane bookkeeping
@@ -243,13 +244,18 @@ extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
     h->max_dyn_smem = optin - 4096 - 1024;  // static reduction scratch + slack
     if (h->max_dyn_smem < 0) h->max_dyn_smem = 0;
     cudaFuncSetAttribute(k_solve_cta<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
+    cudaFuncSetAttribute(k_solve_cta<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
     {   // four CTAs per SM: (SM shared memory - 4 x (static scratch + 1 KB system reservation)) / 4
         int per_sm = 0;
         cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
         int v = (per_sm / 4 - 4096 - 1024) & ~1023;
         h->cta4_smem = v < 16 * 1024 ? 16 * 1024 : v;
+        v = (per_sm / 2 - 4096 - 1024) & ~1023;
+        h->cta2_smem = v < 32 * 1024 ? 32 * 1024 : v;
     }
     cudaFuncSetAttribute(k_solve_cta<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta4_smem);
+    cudaFuncSetAttribute(k_solve_cta<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta4_smem);
+    cudaFuncSetAttribute(k_solve_cta<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta2_smem);
     cudaFuncSetAttribute(k_solve_cta<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024);
     *out = h;
     return 0;
@@ -292,7 +298,7 @@ extern "C" double sqpqp_last_solve_ms(sqpqp_handle h) {
 
 extern "C" int sqpqp_set_options(sqpqp_handle h, const sqpqp_options* o) {
     if (!h || !o) return SQPQP_E_BADARG;
-    if (o->threads < 0 || o->threads > 512 || (o->threads % 32) != 0) return fail(h, SQPQP_E_BADARG, "threads must be a multiple of 32 in [0,512]");
+    if (o->threads < 0 || o->threads > 1024 || (o->threads % 32) != 0) return fail(h, SQPQP_E_BADARG, "threads must be a multiple of 32 in [0,1024]");
     if (o->check_every < 1 || o->max_iter < 1 || !(o->rho0 > 0) || !(o->alpha > 0 && o->alpha < 2)) return fail(h, SQPQP_E_BADARG, "bad option value");
     h->opts = *o;
     return 0;
@@ -484,13 +490,18 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             *dst = d;
             return 0;
         };
-        auto upload_symbolic = [&](const Symbolic& Sy, CholDev& C, int ncols) -> int {
+        auto upload_symbolic = [&](Symbolic& Sy, CholDev& C, int ncols) -> int {
             C.n = ncols; C.nnzL = Sy.nnzL; C.nlev = Sy.nlev; C.n0 = Sy.n0; C.T = Sy.T;
-            const std::vector<int>* srcs[] = {&Sy.perm, &Sy.Lp, &Sy.Li, &Sy.Rp, &Sy.Rmid, &Sy.Rci, &Sy.lev_ptr, &Sy.fp_ptr,
-                                              &Sy.fp_ab, &Sy.tpos, &Sy.as_hd, &Sy.as_abr};
-            const int** dsts[] = {&C.perm, &C.Lp, &C.Li, &C.Rp, &C.Rmid, (const int**)&C.Rci, &C.lev_ptr, &C.fp_ptr,
-                                  (const int**)&C.fp_ab, &C.tpos, (const int**)&C.as_hd, (const int**)&C.as_abr};
-            for (int k = 0; k < 12; ++k) {
+            C.nphase = (int)Sy.fphase.size() / 4; C.n_aoff = (int)Sy.atask_off.size() / 4; C.nslotJ = (int)Sy.jrow.size();
+            for (int k = 0; k < 4; ++k) Sy.fphase.push_back(0);  // the phase loop reads one entry ahead
+            if (Sy.as_ab.empty()) { Sy.as_ab.push_back(0); Sy.as_ab.push_back(0); }
+            if (Sy.ftask.empty()) Sy.ftask.assign(4, 0);
+            const std::vector<int>* srcs[] = {&Sy.perm, &Sy.Lp, &Sy.Li, &Sy.Rp, &Sy.Rmid, &Sy.Rci, &Sy.lev_ptr, &Sy.fp_ab,
+                                              &Sy.ftask, &Sy.fphase, &Sy.atask_off, &Sy.atask_diag, &Sy.as_ab, &Sy.jrow};
+            const int** dsts[] = {&C.perm, &C.Lp, &C.Li, &C.Rp, &C.Rmid, (const int**)&C.Rci, &C.lev_ptr, (const int**)&C.fp_ab,
+                                  (const int**)&C.ftask, (const int**)&C.fphase, (const int**)&C.atask_off,
+                                  (const int**)&C.atask_diag, (const int**)&C.as_ab, &C.jrow};
+            for (int k = 0; k < 14; ++k) {
                 int rc2 = up(*srcs[k], dsts[k]);  // cudaMalloc alignment (256 B) covers the int2 / int4 views
                 if (rc2) return rc2;
             }
@@ -502,14 +513,18 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         // (no CTA-local shared memory across the team) and keeps the plain level-scheduled code.
         auto tail_cap = [&](int ncols) -> int {
             if (batch == 1 && (size_t)P.Ne + m > 6000) return 0;
-            size_t cap = (size_t)h->cta4_smem / sizeof(double);
+            if (const char* ev = getenv("SQPQP_TAIL_MAX")) return atoi(ev);  // development override
+            size_t cap = (size_t)h->cta2_smem / sizeof(double);
             size_t vec = 2 * (size_t)((ncols + 1) & ~1);
             if (vec <= cap / 2) cap -= vec;
             int t = 0;
-            while (t < 128 && (size_t)(t + 1) * (t + 2) / 2 + (size_t)((t + 2) & ~1) <= cap) ++t;
+            // 96 columns: beyond that the dense factorisation of the (only ~40 % full) tail costs more than the
+            // sparse levels it replaces (measured on the case118-shaped batch: T = 48 / 92 / 128 -> 79 / 61 / 67 ms)
+            while (t < 96 && (size_t)(t + 1) * (t + 2) / 2 + (size_t)((t + 2) & ~1) <= cap) ++t;
             return t;
         };
         CUDA_OK(cudaStreamSynchronize(h->stream));
+        DALLOC(P.wJ, B * (size_t)(P.nnzJ > 0 ? P.nnzJ : 1));
         Symbolic Sy = symbolic_analyze(n, m, hJrb.data(), hJre.data(), hJc.data(), hHrp.data(), hHc.data(), 512, tail_cap(n));
         if (Sy.ok && (int64_t)Sy.fp_ab.size() < ((int64_t)1 << 29)) {
             int rc2 = upload_symbolic(Sy, P.chol, n);
@@ -684,27 +699,34 @@ static int launch_solve(sqpqp_handle h, int phase) {
         // re-read through L1, so L1 capacity beats vector residency (measured, profiles/r01_tuning.md).
         const bool many = B >= (size_t)2 * h->num_sms;
         int occ = h->opts.occupancy;  // 0 auto
-        if (occ == 0) occ = many ? 4 : 1;
-        if (!h->opts.threads && many && threads > 256) threads = 256;
+        // measured (profiles/r01_tuning.md): two 512-thread CTAs per SM beat four 256-thread ones (shorter
+        // per-instance latency for the stragglers of a batch) and one 1024-thread CTA (too little work per phase)
+        if (occ == 0) occ = many ? 2 : 1;
+        if (!h->opts.threads && many && threads > 256 && occ != 2) threads = 256;
+        if (!h->opts.threads && occ == 2) threads = 512;
         bool ipm = (phase == SQPQP_PHASE_FR ? P.has_chol_fr : P.has_chol) && h->opts.method != 1;
         const CholDev& CD = (phase == SQPQP_PHASE_FR) ? P.chol_fr : P.chol;
-        size_t budget = occ >= 8 ? 24 * 1024 : (occ >= 4 ? (size_t)h->cta4_smem : (size_t)h->max_dyn_smem);
-        bool vectors = occ < 4;
+        size_t budget = occ >= 8 ? 24 * 1024 : (occ >= 3 ? (size_t)h->cta4_smem : (occ == 2 ? (size_t)h->cta2_smem : (size_t)h->max_dyn_smem));
+        bool vectors = occ < 2;
         if (h->opts.smem_kb >= 0) {  // explicit budget for the vectors (0 = none)
             vectors = h->opts.smem_kb > 0;
             if ((size_t)h->opts.smem_kb * 1024 < budget && vectors) budget = (size_t)h->opts.smem_kb * 1024;
         }
         Placement pl;
         place_arrays(P, phase, budget, ipm, vectors, &pl);
-        if (ipm && CD.T > 0 && pl.dtail < 0 && occ >= 8) {  // the tail was sized for four CTAs per SM
-            occ = 4;
-            budget = (size_t)h->cta4_smem;
+        if (ipm && CD.T > 0 && pl.dtail < 0 && occ >= 3) {  // the tail was sized for two CTAs per SM
+            occ = 2;
+            if (threads < 512 && !h->opts.threads) threads = 512;
+            budget = (size_t)h->cta2_smem;
             place_arrays(P, phase, budget, ipm, vectors, &pl);
         }
         if (ipm && CD.T > 0 && pl.dtail < 0) return fail(h, SQPQP_E_STATE, "dense tail of the factor does not fit the shared-memory budget of this launch configuration");
         size_t dyn = (size_t)pl.total * sizeof(double);
         if (occ >= 8 && threads <= 128) k_solve_cta<128, 8><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
         else if (occ >= 4 && threads <= 256) k_solve_cta<256, 4><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+        else if (occ == 3 && threads <= 256) k_solve_cta<256, 3><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+        else if (occ >= 2 && threads <= 512) k_solve_cta<512, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+        else if (threads > 512) k_solve_cta<1024, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
         else k_solve_cta<512, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
     }
     h->launches++;

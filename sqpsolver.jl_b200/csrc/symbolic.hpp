@@ -36,11 +36,18 @@ struct Symbolic {
     std::vector<int> lev_ptr;            // [nlev+1] column range of each sparse level
     std::vector<int> fp_ptr;             // per entry id: range in fp_ab
     std::vector<int> fp_ab;              // interleaved pairs of L value indices to multiply-subtract
-    std::vector<int> tpos;               // per tail entry (id - Lp[n0]): position in the packed dense tail
-    // assembly program
-    std::vector<int> as_hd;              // per entry id, interleaved (P value index or -1, original column for d[] or -1,
-                                         //                            begin, end of its terms in as_abr)
-    std::vector<int> as_abr;             // per term, interleaved (Jv index a, Jv index b, row = weight index, 0)
+    // factorisation as a list of barrier phases over flat task lists (4 ints each):
+    //   task  = (entry id | has_K << 30, first pair, end pair, aux)   aux: column (diag/offdiag) or packed tail position (Schur)
+    //   phase = (first task, end task, max pairs of a task, kind)     kind: 0 diagonal entries of a level, 1 sub-diagonal
+    //           entries of a level, 2 Schur complement of the dense tail.   Tasks of a phase are sorted by pair count
+    //           (descending) so that the sub-warps of one round carry similar work.
+    std::vector<int> ftask, fphase;
+    // assembly: K_e = P[h] + sum_t wJ[a_t] * Jv[b_t]  (+ d[perm[j]] on the diagonal), wJ = w[row] .* Jv
+    std::vector<int> atask_off;          // sourced sub-diagonal entries: (entry id, first term, end term, P value index | -1)
+    std::vector<int> atask_diag;         // per column j: (entry id, first term, end term, P value index | -1)
+    std::vector<int> as_ab;              // interleaved (Jv index a, Jv index b) per term
+    std::vector<int> jrow;               // row of every J value slot (for wJ); slots beyond a row's end: -1
+    int as_terms = 0;
     int64_t flops = 0;                   // of the sparse part (2 * pairs)
     bool ok = false;                     // false: a row of J is too long for the clique expansion
 };
@@ -197,17 +204,9 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
             S.flops = 2 * total;
         }
     }
-    // packed position (row-major lower triangle of the T x T tail) of every tail entry
-    S.tpos.clear();
-    for (int j = n0; j < n; ++j)
-        for (int p = S.Lp[j]; p < S.Lp[j + 1]; ++p) {
-            int r = S.Li[p] - n0, c = j - n0;
-            S.tpos.push_back(r * (r + 1) / 2 + c);
-        }
-
     // ---- 4b. assembly program --------------------------------------------------------------------
     // map (i,j) permuted, i>=j -> entry id
-    std::vector<int> as_h(S.nnzL, -1), as_d(S.nnzL, -1);
+    std::vector<int> as_h(S.nnzL, -1);
     auto find_entry = [&](int a, int b) {  // original indices
         int i = S.iperm[a], j = S.iperm[b];
         if (i < j) std::swap(i, j);
@@ -217,7 +216,6 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
         const int* it = std::lower_bound(lo, hi, i);
         return (int)(it - &S.Li[0]);
     };
-    for (int k = 0; k < n; ++k) as_d[S.Lp[k]] = S.perm[k];
     if (Prp)
         for (int a = 0; a < n; ++a)
             for (int k = Prp[a]; k < Prp[a + 1]; ++k) {
@@ -236,20 +234,66 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
                     if (!pass) cnt[e + 1]++;
                     else {
                         size_t pos = (size_t)as_ptr[e] + cnt[e]++;
-                        S.as_abr[4 * pos] = a; S.as_abr[4 * pos + 1] = b; S.as_abr[4 * pos + 2] = r; S.as_abr[4 * pos + 3] = 0;
+                        S.as_ab[2 * pos] = a; S.as_ab[2 * pos + 1] = b;
                     }
                 }
         if (!pass) {
             as_ptr.assign(S.nnzL + 1, 0);
             for (int e = 0; e < S.nnzL; ++e) as_ptr[e + 1] = as_ptr[e] + cnt[e + 1];
-            S.as_abr.resize(4 * (size_t)as_ptr[S.nnzL]);
+            S.as_ab.resize(2 * (size_t)as_ptr[S.nnzL]);
+            S.as_terms = as_ptr[S.nnzL];
             std::fill(cnt.begin(), cnt.end(), 0);
         }
     }
-    S.as_hd.resize(4 * (size_t)S.nnzL);
-    for (int e = 0; e < S.nnzL; ++e) {
-        S.as_hd[4 * (size_t)e] = as_h[e]; S.as_hd[4 * (size_t)e + 1] = as_d[e];
-        S.as_hd[4 * (size_t)e + 2] = as_ptr[e]; S.as_hd[4 * (size_t)e + 3] = as_ptr[e + 1];
+    std::vector<char> hasK(S.nnzL, 0);
+    S.atask_diag.clear();
+    S.atask_off.clear();
+    for (int j = 0; j < n; ++j)
+        for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
+            const bool diag = e == S.Lp[j];
+            if (!diag && as_h[e] < 0 && as_ptr[e] == as_ptr[e + 1]) continue;  // pure fill: K_e = 0, nothing to assemble
+            hasK[e] = 1;
+            std::vector<int>& dst = diag ? S.atask_diag : S.atask_off;
+            dst.push_back(e); dst.push_back(as_ptr[e]); dst.push_back(as_ptr[e + 1]); dst.push_back(as_h[e]);
+        }
+    {
+        int nslots = 0;
+        for (int r = 0; r < m; ++r) nslots = std::max(nslots, Jre[r]);
+        for (int r = 0; r < m; ++r) nslots = std::max(nslots, Jrb[r]);
+        S.jrow.assign(nslots, -1);
+        for (int r = 0; r < m; ++r)
+            for (int a = Jrb[r]; a < Jre[r]; ++a) S.jrow[a] = r;
+    }
+    // ---- 4c. factorisation phases ----------------------------------------------------------------
+    {
+        struct Tk { int tgt, q0, q1, aux; };
+        auto emit = [&](std::vector<Tk>& v, int kind) {
+            std::stable_sort(v.begin(), v.end(), [](const Tk& a, const Tk& b) { return a.q1 - a.q0 > b.q1 - b.q0; });
+            int t0 = (int)S.ftask.size() / 4, mp = 0;
+            for (const Tk& t : v) {
+                S.ftask.push_back(t.tgt | (hasK[t.tgt] ? (1 << 30) : 0)); S.ftask.push_back(t.q0); S.ftask.push_back(t.q1); S.ftask.push_back(t.aux);
+                mp = std::max(mp, t.q1 - t.q0);
+            }
+            S.fphase.push_back(t0); S.fphase.push_back(t0 + (int)v.size()); S.fphase.push_back(mp); S.fphase.push_back(kind);
+            v.clear();
+        };
+        std::vector<Tk> v;
+        for (int l = 0; l < S.nlev; ++l) {
+            for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j) v.push_back(Tk{S.Lp[j], S.fp_ptr[S.Lp[j]], S.fp_ptr[S.Lp[j] + 1], j});
+            emit(v, 0);
+            for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j)
+                for (int e = S.Lp[j] + 1; e < S.Lp[j + 1]; ++e) v.push_back(Tk{e, S.fp_ptr[e], S.fp_ptr[e + 1], j});
+            if (!v.empty()) emit(v, 1);
+        }
+        if (S.T > 0) {
+            // packed position (row-major lower triangle of the T x T tail) of every tail entry
+            for (int j = n0; j < n; ++j)
+                for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
+                    int r = S.Li[e] - n0, c = j - n0;
+                    v.push_back(Tk{e, S.fp_ptr[e], S.fp_ptr[e + 1], r * (r + 1) / 2 + c});
+                }
+            emit(v, 2);
+        }
     }
     S.ok = true;
     return S;

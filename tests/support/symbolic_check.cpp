@@ -17,45 +17,55 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
     Symbolic S = symbolic_analyze(n, m, Jrp, Jrp + 1, Jcol, Prp, Pcol, 512, tail_max);
     if (!S.ok) return -1;
     const int n0 = S.n0, T = S.T;
-    std::vector<double> L(S.nnzL), D((size_t)tri(T) + T, 0.0), dinv(n);
-    for (int e = 0; e < S.nnzL; ++e) {
-        double v = 0.0;
-        const int* hd = &S.as_hd[4 * (size_t)e];
-        if (hd[0] >= 0) v += Pv[hd[0]];
-        if (hd[1] >= 0) v += d[hd[1]];
-        for (int t = hd[2]; t < hd[3]; ++t) {
-            const int* abr = &S.as_abr[4 * (size_t)t];
-            v += w[abr[2]] * Jv[abr[0]] * Jv[abr[1]];
-        }
-        L[e] = v;
-    }
-    auto pairs = [&](int e) {
-        double acc = 0.0;
-        for (int q = S.fp_ptr[e]; q < S.fp_ptr[e + 1]; ++q) acc += L[S.fp_ab[2 * (size_t)q]] * L[S.fp_ab[2 * (size_t)q + 1]];
-        return acc;
+    std::vector<double> L(S.nnzL, std::nan("")), D((size_t)tri(T) + T, 0.0), dinv(n), wJ(S.jrow.size());
+    // assembly (chol_assemble): wJ, then the diagonal and the sourced sub-diagonal entries; pure fill stays unset (NaN here:
+    // a factor task that read it although has_K = 0 would poison the result)
+    for (size_t a = 0; a < S.jrow.size(); ++a) wJ[a] = S.jrow[a] >= 0 ? w[S.jrow[a]] * Jv[a] : 0.0;
+    auto assemble = [&](const int* tk, bool diag, int col) {
+        double v = (Pv && tk[3] >= 0) ? Pv[tk[3]] : 0.0;
+        if (diag) v += d[S.perm[col]];
+        for (int t = tk[1]; t < tk[2]; ++t) v += wJ[S.as_ab[2 * (size_t)t]] * Jv[S.as_ab[2 * (size_t)t + 1]];
+        L[tk[0]] = v;
     };
-    for (int l = 0; l < S.nlev; ++l)
-        for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j) {
-            int e0 = S.Lp[j];
-            double dd = L[e0] - pairs(e0);
-            if (!(dd > 0.0)) return -2;
-            double inv = 1.0 / std::sqrt(dd);
-            for (int e = e0 + 1; e < S.Lp[j + 1]; ++e) L[e] = (L[e] - pairs(e)) * inv;
-            L[e0] = dd * inv;
-            dinv[j] = inv;
+    if ((int)S.atask_diag.size() != 4 * n) return -4;
+    for (int j = 0; j < n; ++j) assemble(&S.atask_diag[4 * (size_t)j], true, j);
+    for (size_t t = 0; t < S.atask_off.size() / 4; ++t) assemble(&S.atask_off[4 * t], false, 0);
+    // factorisation phases (chol_factor)
+    for (size_t p = 0; p < S.fphase.size() / 4; ++p) {
+        const int* ph = &S.fphase[4 * p];
+        for (int t = ph[0]; t < ph[1]; ++t) {
+            const int* tk = &S.ftask[4 * (size_t)t];
+            const int e = tk[0] & 0x3fffffff;
+            double acc = 0.0;
+            if (tk[2] - tk[1] > ph[2]) return -5;
+            for (int q = tk[1]; q < tk[2]; ++q) acc += L[S.fp_ab[2 * (size_t)q]] * L[S.fp_ab[2 * (size_t)q + 1]];
+            double v = ((tk[0] >> 30) ? L[e] : 0.0) - acc;
+            if (ph[3] == 0) {
+                if (!(v > 0.0)) return -2;
+                double inv = 1.0 / std::sqrt(v);
+                L[e] = v * inv;
+                dinv[tk[3]] = inv;
+            } else if (ph[3] == 1) {
+                L[e] = v * dinv[tk[3]];
+            } else {
+                D[tk[3]] = v;
+            }
         }
+    }
     if (S.nlev > 0 && S.lev_ptr[S.nlev] != n0) return -3;
-    if (T > 0) {
-        const int base = S.Lp[n0];
-        for (int e = base; e < S.nnzL; ++e) D[S.tpos[e - base]] = L[e] - pairs(e);
+    if (T > 0) {  // left-looking dense Cholesky of the packed tail (dense_factor)
         for (int j = 0; j < T; ++j) {
-            double dd = D[tri(j) + j];
-            if (!(dd > 0.0)) return -2;
-            double inv = 1.0 / std::sqrt(dd);
+            double dj = 0.0;
+            for (int k = 0; k < j; ++k) dj += D[tri(j) + k] * D[tri(j) + k];
+            double pv = D[tri(j) + j] - dj;
+            if (!(pv > 0.0)) return -2;
+            double inv = 1.0 / std::sqrt(pv);
             dinv[n0 + j] = inv;
-            for (int i = j + 1; i < T; ++i) D[tri(i) + j] *= inv;
-            for (int i = j + 1; i < T; ++i)
-                for (int k = j + 1; k <= i; ++k) D[tri(i) + k] -= D[tri(i) + j] * D[tri(k) + j];
+            for (int i = j + 1; i < T; ++i) {
+                double di = 0.0;
+                for (int k = 0; k < j; ++k) di += D[tri(i) + k] * D[tri(j) + k];
+                D[tri(i) + j] = (D[tri(i) + j] - di) * inv;
+            }
         }
     }
     std::vector<double> y(n);
@@ -88,7 +98,7 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
     }
     for (int k = 0; k < n; ++k) x[S.perm[k]] = y[k];
     if (stats) {
-        stats[0] = S.nnzL; stats[1] = S.nlev; stats[2] = S.flops; stats[3] = (int64_t)S.as_abr.size() / 4;
+        stats[0] = S.nnzL; stats[1] = S.nlev; stats[2] = S.flops; stats[3] = S.as_terms;
         stats[4] = S.T; stats[5] = S.nlev_total;
     }
     return 0;

@@ -22,8 +22,9 @@ def hook(phase, x_k, delta, E_override=None, active=None):
     i = info[act]
     fb = int((i['admm_iters'] > 0).sum())
     print(f"round {sqp.rounds:3d} phase {phase} active {int(act.sum()):4d} ms {sqp.optimizer.engine.last_solve_ms:8.1f} ipm it mean {i['ipm_iters'].mean():5.1f} max {i['ipm_iters'].max():3d} nfact max {i['chol_factorizations'].max():3d} fallbacks {fb} status {dict(zip(*np.unique(i['moi_status'], return_counts=True)))}", flush=True)
-    if fb and len(bad) < 4:
-        b = int(np.nonzero(act & (info['admm_iters'] > 0))[0][0])
+    slow = int(np.argmax(np.where(act, info['ipm_iters'], -1)))
+    if (fb or info['ipm_iters'][slow] >= 60) and len(bad) < 6:
+        b = int(np.nonzero(act & (info['admm_iters'] > 0))[0][0]) if fb else slow
         bad.append({'b': b, 'iter': int(sqp.iter[b]), 'fr': phase == 1, 'x': sqp.x[b].copy(), 'Delta': float(sqp.Delta[b]), 'dE': sqp.dE[b].copy(), 'h_val': sqp.h_val[b].copy(), 'df': sqp.df[b].copy(), 'E': sqp.E[b].copy(), 'pd': pd[b].copy(), 'qd': qd[b].copy(), 'status': int(info['moi_status'][b])})
     return out
 sqp.optimizer._solve = hook

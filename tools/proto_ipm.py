@@ -32,6 +32,10 @@ class Opts:
     monotone = True
     mu0 = 1.0
     kappa_eps = 10.0
+    rho_dec = 3.0      # decay of the inertia-correction shift per iteration
+    rho_bump = 10.0    # growth on a failed factorisation
+    rho_hold = 0       # iterations the shift is held after a failed factorisation
+    rho_floor_frac = 0.0  # never decay below this fraction of the last shift that was NEEDED
 
 
 class _SymLU:
@@ -102,6 +106,8 @@ def ipm_solve(P, q, J, rl, ru, xl, xu, o: Opts = Opts()):
     mu_t = o.mu0
     status = "MAX_ITER"
     nfact = 0
+    hold = 0
+    rho_need = 0.0
     for it in range(o.max_iter):
         Ax = Js @ x
         Px = Ps @ x
@@ -138,7 +144,9 @@ def ipm_solve(P, q, J, rl, ru, xl, xu, o: Opts = Opts()):
             nfact += 1
             if ok:
                 break
-            rho_p = max(10.0 * rho_p, 1e-4 if rho_last == 0.0 else rho_last / 3.0, 1e-6)
+            hold = o.rho_hold
+            rho_p = max(o.rho_bump * rho_p, 1e-4 if rho_last == 0.0 else rho_last / 3.0, 1e-6)
+            rho_need = rho_p
             if rho_p > 1e8:
                 return {"status": "NUMERICAL", "x": D * x, "info": dict(iters=it, nfact=nfact)}
         if rho_p > o.rho0 * 10:
@@ -190,8 +198,10 @@ def ipm_solve(P, q, J, rl, ru, xl, xu, o: Opts = Opts()):
             s_ru, s_rl, s_xu, s_xl = [s + a * ds for s, ds in zip(S, dS)]
             z_ru, z_rl, z_xu, z_xl = [z + a * dz for z, dz in zip(Z, dZ)]
             delta = max(o.delta_min, delta * 0.3)
-            if rho_p > o.rho0:
-                rho_p = max(o.rho0, rho_p / 3.0)
+            if hold > 0:
+                hold -= 1
+            elif rho_p > o.rho0:
+                rho_p = max(o.rho0, rho_p / o.rho_dec, o.rho_floor_frac * rho_need)
             continue
         # predictor (affine): rc = -s z
         aff = solve_dir(*[-s * z for s, z in zip(S, Z)])
