@@ -90,6 +90,54 @@ def algorithmic_bytes(info, sel, n, m, nnzJ, nnzH, chol=None):
     return tot
 
 
+def spmv_roofline(local, dev, peak, batch, reps=10):
+    """SpMV leg of BASELINE.json's metric: the three CSR products of the path (J p, J' lambda, H p;
+    sqp_trust_region.jl:343,490,492, common.jl:17) through csrc/spmv.cuh on the ~2000-bus synthetic network
+    (BASELINE configs[3]), batched so that the value streams (batch x nnz x 8 B) exceed the 126 MB L2.
+    achieved = algorithmic bytes (fp64 values + x + y per instance, int32 pattern once) / CUDA-event time."""
+    import torch
+    from sqpsolver_jl_b200 import capi
+    from sqpsolver_jl_b200.nlp.acopf import AcopfPolar
+    from sqpsolver_jl_b200.nlp.networks import synth_net
+
+    net = synth_net(2000, 3000, 400, seed=2000)
+    nlp = AcopfPolar(net)
+    eng = capi.Engine(local)
+    try:
+        eng.setup_nlp(nlp.n, nlp.m, nlp.num_linear_constraints, nlp.j_row, nlp.j_col, nlp.h_row, nlp.h_col,
+                      nlp.x_L, nlp.x_U, nlp.g_L, nlp.g_U, batch=batch)
+        rng = np.random.default_rng(2000)
+        dE = rng.standard_normal((1, nlp.nnz_jac_coo)) + 1e-3 * rng.standard_normal((batch, 1))
+        hv = rng.standard_normal((1, nlp.nnz_hess_coo)) + 1e-3 * rng.standard_normal((batch, 1))
+        eng.update_nlp(dE, hv, np.zeros((batch, nlp.n)), np.zeros((batch, nlp.m)))
+        nnz = {0: int(eng.get_csr(0)[1].shape[0]), 2: int(eng.get_csr(2)[1].shape[0])}
+        nnz[1] = nnz[0]
+        dims = {0: (nlp.m, nlp.n), 1: (nlp.n, nlp.m), 2: (nlp.n, nlp.n)}
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        out = {}
+        for which, name in ((0, "J*x"), (1, "J'*y"), (2, "H*x")):
+            rows, cols = dims[which]
+            x = torch.randn(batch, cols, dtype=torch.float64, device=dev)
+            y = torch.empty(batch, rows, dtype=torch.float64, device=dev)
+            ms = []
+            for it in range(3 + reps):
+                flush.fill_(it & 0xFF)
+                torch.cuda.synchronize()
+                eng.spmv_device(which, x.data_ptr(), y.data_ptr())
+                t = eng.last_solve_ms  # events recorded on the engine's stream around the launch
+                if it >= 3:
+                    ms.append(t)
+            byt = batch * 8 * (nnz[which] + rows + cols) + 4 * nnz[which] + 8 * rows
+            t_avg = float(np.mean(ms))
+            out[name] = {"rows": rows, "cols": cols, "nnz": nnz[which], "ms": t_avg, "GBps": byt / (t_avg * 1e-3) / 1e9,
+                         "frac": byt / (t_avg * 1e-3) / 1e9 / peak if peak else None}
+        return {"workload": "ACOPF ~2000-bus synthetic network (n=%d, m=%d), %d instances with one shared pattern" % (nlp.n, nlp.m, batch),
+                "kernel": "k_spmv_stream (CSR-stream, csrc/spmv.cuh)", "reps": reps, "l2": "256 MiB flush before every launch",
+                "peak_GBps": peak, "products": out}
+    finally:
+        eng.close()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
 
@@ -211,6 +259,8 @@ def main():
     ap.add_argument("--sqp-max-iter", dest="sqp_max_iter", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=12, help="QP subproblems solved by the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-spmv", action="store_true", help="skip the 2000-bus SpMV roofline leg")
+    ap.add_argument("--spmv-batch", type=int, default=512)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -226,6 +276,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
@@ -418,6 +472,8 @@ def main():
             "full_sqp_solve": full,
             "results_gathered": {"instances": int(res_all.shape[0]), "status_counts": {int(k): int(v) for k, v in zip(*np.unique(res_all["status"], return_counts=True))}},
         }
+        if not args.no_spmv and world == 1:
+            line["spmv"] = spmv_roofline(local, dev, peak, args.spmv_batch)
         if not args.no_cpu_baseline and world == 1:
             tcb0 = time.perf_counter()
             times = []
@@ -434,7 +490,10 @@ def main():
                 line["cpu_baseline"] = {"value": len(times) / float(np.sum(times)), "unit": UNIT, "cores": 1, "kind": "port",
                                         "sample": f"{len(times)} of the replayed QP subproblems (instances 0.. of rounds 1..{R}) solved one "
                                                   "after another by the CPU oracle (SciPy/SuperLU interior point, not Ipopt)"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

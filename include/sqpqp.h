@@ -187,6 +187,13 @@ int sqpqp_kt_residuals(sqpqp_handle h, const double* lambda, const double* mult_
 
 /* out[batch][m] = J p per instance (`Jacobian * p`, sqp_trust_region.jl:343, 492). */
 int sqpqp_jac_times(sqpqp_handle h, const double* p, double* out);
+/* Batched CSR sparse matrix-vector products on the current device matrices, one shared pattern
+ * (csrc/spmv.cuh, CSR-stream): which = 0: y[batch][m] = J x (sqp_trust_region.jl:343,492),
+ * 1: y[batch][n] = J' x (common.jl:17), 2: y[batch][n] = H x (sqp_trust_region.jl:490).
+ * sqpqp_spmv takes host buffers and blocks; sqpqp_spmv_device takes device pointers, does not
+ * block, and is timed by sqpqp_last_solve_ms. */
+int sqpqp_spmv(sqpqp_handle h, int32_t which, const double* x, double* y);
+int sqpqp_spmv_device(sqpqp_handle h, int32_t which, const double* x_dev, double* y_dev);
 
 /* Read back the device matrices of instance b (parity tests): CSR of J (m x n, slack
  * columns excluded), CSR of J' (n x m) and symmetric CSR of H.  Pass NULL to skip.

@@ -82,7 +82,7 @@ EXPORTS = [
     "sqpqp_setup_nlp", "sqpqp_update_nlp", "sqpqp_update_nlp_device", "sqpqp_solve_tr", "sqpqp_num_slacks",
     "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
     "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
-    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read",
+    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device",
 ]
 
 
@@ -139,6 +139,8 @@ def lib():
     L.sqpqp_chol_stats.argtypes = [vp, _lp, _lp, _lp]
     L.sqpqp_chol_layout.argtypes = [vp, _lp, _lp]
     L.sqpqp_prof_read.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.sqpqp_spmv.argtypes = [vp, C.c_int32, _dp, _dp]
+    L.sqpqp_spmv_device.argtypes = [vp, C.c_int32, vp, vp]
     L.sqpqp_num_slacks.argtypes = [vp, _ip]
     L.sqpqp_merit.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp]
     L.sqpqp_kt_residuals.argtypes = [vp, _dp, _dp, _dp, _dp]
@@ -285,6 +287,19 @@ class Engine:
         t, lv = C.c_int64(), C.c_int64()
         self._ck(self.L.sqpqp_chol_layout(self.h, C.byref(t), C.byref(lv)))
         return {"nnzL": a.value, "levels": b.value, "flops": c.value, "dense_tail": t.value, "tree_levels": lv.value}
+
+    def spmv(self, which, x):
+        """y = J x (which=0), J' x (1), H x (2) per instance on the device matrices; host arrays in and out."""
+        B = self.batch
+        nx = self.m if which == 1 else self.n
+        ny = self.m if which == 0 else self.n
+        x = _f64(x).reshape(B, nx)
+        y = np.empty((B, ny))
+        self._ck(self.L.sqpqp_spmv(self.h, which, _d(x), _d(y)))
+        return y
+
+    def spmv_device(self, which, x_dev_ptr, y_dev_ptr):
+        self._ck(self.L.sqpqp_spmv_device(self.h, which, C.c_void_p(int(x_dev_ptr)), C.c_void_p(int(y_dev_ptr))))
 
     def prof_read(self):
         """Cycles per solve segment (csrc/common.cuh ProfSeg) since the last call; zeros in a normal build."""

@@ -71,11 +71,12 @@ __device__ __forceinline__ double column_dot(const double* __restrict__ V, const
 }
 
 // L <- lower triangle of K in the permuted order, sourced entries only (pure fill entries have
-// K_e = 0 and are never read: their factor task carries has_K = 0).  Pv may be null (no P); dg[j] is
-// added to the diagonal entry of ORIGINAL column j.  Also clears the dense tail.
+// K_e = 0 and are never read: their factor task carries has_K = 0).  Pv may be null (no P); dg[j] + shift
+// is added to the diagonal entry of ORIGINAL column j.  Also clears the dense tail.
 template <class Team>
 __device__ void chol_assemble(Team& T, const CholDev& C, const CholWork& W, const double* __restrict__ Pv,
-                              const double* __restrict__ dg, const double* __restrict__ w, const double* __restrict__ Jv) {
+                              const double* __restrict__ dg, const double shift, const double* __restrict__ w,
+                              const double* __restrict__ Jv) {
     double* __restrict__ L = W.L;
     double* __restrict__ wJ = W.wJ;
     for (int a = T.tid(); a < C.nslotJ; a += T.size()) {
@@ -96,8 +97,8 @@ __device__ void chol_assemble(Team& T, const CholDev& C, const CholWork& W, cons
         const int4 k2 = has2 ? (t2 < C.n ? C.atask_diag[t2] : C.atask_off[t2 - C.n]) : make_int4(0, 0, 0, -1);
         double v1 = (Pv && k1.w >= 0) ? Pv[k1.w] : 0.0;
         double v2 = (Pv && k2.w >= 0) ? Pv[k2.w] : 0.0;
-        if (t < C.n) v1 += dg[C.perm[t]];
-        if (has2 && t2 < C.n) v2 += dg[C.perm[t2]];
+        if (t < C.n) v1 += dg[C.perm[t]] + shift;
+        if (has2 && t2 < C.n) v2 += dg[C.perm[t2]] + shift;
         int q1 = k1.y, q2 = k2.y;
         const int e1 = k1.z, e2 = k2.z;
         while (q1 < e1 || q2 < e2) {

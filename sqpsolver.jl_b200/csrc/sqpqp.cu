@@ -17,6 +17,7 @@
 #include "admm.cuh"
 #include "ipm.cuh"
 #include "merit.cuh"
+#include "spmv.cuh"
 #include "symbolic.hpp"
 
 struct Pending {
@@ -55,6 +56,7 @@ struct sqpqp_handle_s {
     int cta2_smem = 100 * 1024; // ... when two share an SM (the default for large batches)
     int64_t chol_flops = 0;
     std::vector<double> avg_row;  // avg row length of J(normal), J(ext), T, H
+    SpmvPlan planJ{}, planT{}, planH{};  // CSR-stream row blocks of J (normal phase), J' and H
     // generic-lane bookkeeping
     bool generic = false;
 };
@@ -524,6 +526,21 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             return t;
         };
         CUDA_OK(cudaStreamSynchronize(h->stream));
+        {   // CSR-stream SpMV plans (spmv.cuh): row blocks of <= SPMV_CHUNK value slots, shared by the batch
+            std::vector<int> hTrp(n + 1), blk;
+            CUDA_OK(cudaMemcpy(hTrp.data(), pt.row_ptr, (n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+            const int* d = nullptr;
+            int rc2;
+            spmv_blocks(m, hJrb.data(), hJre.data(), blk);
+            if ((rc2 = up(blk, &d))) return rc2;
+            h->planJ = SpmvPlan{(int)blk.size() - 1, d, pj.row_ptr, re_n, pj.col_idx, n, m, P.nnzJ};
+            spmv_blocks(n, hTrp.data(), hTrp.data() + 1, blk);
+            if ((rc2 = up(blk, &d))) return rc2;
+            h->planT = SpmvPlan{(int)blk.size() - 1, d, pt.row_ptr, pt.row_ptr + 1, pt.col_idx, m, n, P.nnzT};
+            spmv_blocks(n, hHrp.data(), hHrp.data() + 1, blk);
+            if ((rc2 = up(blk, &d))) return rc2;
+            h->planH = SpmvPlan{(int)blk.size() - 1, d, ph.row_ptr, ph.row_ptr + 1, ph.col_idx, n, n, P.nnzH};
+        }
         DALLOC(P.wJ, B * (size_t)(P.nnzJ > 0 ? P.nnzJ : 1));
         Symbolic Sy = symbolic_analyze(n, m, hJrb.data(), hJre.data(), hJc.data(), hHrp.data(), hHc.data(), 512, tail_cap(n));
         if (Sy.ok && (int64_t)Sy.fp_ab.size() < ((int64_t)1 << 29)) {
@@ -882,6 +899,19 @@ extern "C" int sqpqp_kt_residuals(sqpqp_handle h, const double* lambda, const do
     return finish(h);
 }
 
+// which: 0 y = J x (m <- n), 1 y = J' x (n <- m), 2 y = H x (n <- n); device pointers, [batch][len]
+static int launch_spmv(sqpqp_handle h, int which, const double* x, double* y) {
+    Prob& P = h->P;
+    const SpmvPlan& S = which == 0 ? h->planJ : (which == 1 ? h->planT : h->planH);
+    const double* vals = which == 0 ? P.Jv : (which == 1 ? P.Tv : P.Hv);
+    if (S.nblocks <= 0 || S.nrows <= 0) return 0;
+    int gy = P.batch < 65535 ? P.batch : 65535;
+    k_spmv_stream<<<dim3(S.nblocks, gy), SPMV_THREADS, 0, h->stream>>>(S, vals, x, y, which == 1 ? P.m : P.n, P.batch);
+    h->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int sqpqp_jac_times(sqpqp_handle h, const double* p, double* out) {
     if (!h) return SQPQP_E_BADARG;
     if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
@@ -895,9 +925,41 @@ extern "C" int sqpqp_jac_times(sqpqp_handle h, const double* p, double* out) {
     size_t off = h->stage_off;
     h->stage_off = align256(off + B * P.m * sizeof(double));
     double* dout = (double*)(h->dstage + off);
-    k_jac_times<<<(int)(B < 65535 ? B : 65535), 128, 0, h->stream>>>(P, dp, dout);
-    h->launches++;
+    rc = launch_spmv(h, 0, dp, dout);
+    if (rc) return rc;
     download(h, dout, out, B * P.m);
+    return finish(h);
+}
+
+extern "C" int sqpqp_spmv_device(sqpqp_handle h, int32_t which, const double* x_dev, double* y_dev) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
+    if (which < 0 || which > 2 || !x_dev || !y_dev) return fail(h, SQPQP_E_BADARG, "bad selector or null pointer");
+    DeviceGuard g(h->device);
+    CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+    int rc = launch_spmv(h, which, x_dev, y_dev);
+    if (rc) return rc;
+    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+    h->timing_pending = true;
+    return 0;
+}
+
+extern "C" int sqpqp_spmv(sqpqp_handle h, int32_t which, const double* x, double* y) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
+    if (which < 0 || which > 2 || !x || !y) return fail(h, SQPQP_E_BADARG, "bad selector or null pointer");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    const size_t B = P.batch, nx = which == 1 ? P.m : P.n, ny = which == 0 ? P.m : P.n;
+    int rc = ensure_stage(h, B * (nx + ny + 8) * sizeof(double) * 2 + 16384);
+    if (rc) return rc;
+    const double* dx = upload(h, x, B * nx);
+    size_t off = h->stage_off;
+    h->stage_off = align256(off + B * ny * sizeof(double));
+    double* dy = (double*)(h->dstage + off);
+    rc = launch_spmv(h, which, dx, dy);
+    if (rc) return rc;
+    download(h, dy, y, B * ny);
     return finish(h);
 }
 

@@ -15,6 +15,7 @@ cases = {
     'case9_default': (lambda: AcopfPolar(case9()), dict(max_iter=100)),
     'case9_soc': (lambda: AcopfPolar(case9()), dict(max_iter=100, init_mu=1e4, use_soc=True)),
     'c118': (lambda: AcopfPolar(synth_net(118, 186, 54, 118)), dict(max_iter=100, init_mu=1e5)),
+    'c2000': (lambda: AcopfPolar(synth_net(2000, 3000, 400, 2000)), dict(max_iter=int(os.environ.get('C2000_ITERS', '3')), init_mu=1e5)),
 }
 if __name__ == "__main__":
     names = sys.argv[1].split(',') if len(sys.argv) > 1 else ['toy', 'readme', 'case9']
