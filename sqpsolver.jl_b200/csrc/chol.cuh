@@ -83,8 +83,12 @@ __device__ void chol_assemble(Team& T, const CholDev& C, const CholWork& W, cons
         const int r = C.jrow[a];
         wJ[a] = r >= 0 ? w[r] * Jv[a] : 0.0;
     }
-    if (C.T > 0)
-        for (int i = T.tid(); i < C.T * (C.T + 1) / 2; i += T.size()) W.D[i] = 0.0;
+    if (C.T > 0) {  // packed tail, padded to a multiple of 4 columns with identity rows (dense_factor works in panels of 4)
+        const int Tp = (C.T + 3) & ~3;
+        for (int i = T.tid(); i < Tp * (Tp + 1) / 2; i += T.size()) W.D[i] = 0.0;
+        T.sync();
+        for (int i = C.T + T.tid(); i < Tp; i += T.size()) W.D[i * (i + 1) / 2 + i] = 1.0;
+    }
     T.sync();
     // two tasks per thread and round, their (short) term lists walked together so that both gather
     // chains are in flight
@@ -119,43 +123,66 @@ __device__ void chol_assemble(Team& T, const CholDev& C, const CholWork& W, cons
 // packed row-major lower triangle: (r, c), c <= r, at r (r + 1) / 2 + c
 __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 
-// Left-looking dense Cholesky of the packed D (T x T): in step j a sub-warp per remaining row i >= j
-// forms  S_ij - sum_{k<j} L_ik L_jk  and -- redundantly, it streams row j anyway --  the pivot
-// S_jj - sum_{k<j} L_jk^2, so one barrier per column suffices.  The lanes per row grow as the rows
-// run out (the dots get longer as the rows get fewer).  D[j][j] keeps S_jj; 1/L_jj goes to dinvT.
-// Returns 1.0 if a pivot was not positive (uniform: every sub-warp sees the same pivots).
+// Right-looking dense Cholesky of the packed D in panels of 4 columns.  Tp = T rounded up to a multiple
+// of 4 (the padding rows are identity: chol_assemble sets them).  Per panel:
+//   A. every thread reads the 4 x 4 diagonal block (10 broadcast loads) and factorises it in registers --
+//      redundantly, which costs no barrier; thread r then forward-substitutes row j0 + 4 + r of the panel
+//      (4 values) against it, thread 0 stores the block's factor and the inverse pivots;
+//   B. after one barrier the trailing matrix gets its rank-4 update, a warp per row, a lane per column.
+// Two barriers per 4 columns, no reductions (the per-column variant needs a barrier, a shuffle
+// reduction and a dependent rsqrt for every column).  Returns 1.0 if a pivot was not positive
+// (uniform: every thread factorises the same diagonal blocks).
 __device__ inline double dense_factor(double* __restrict__ D, double* __restrict__ dinvT, int Tn) {
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, wp = tid >> 5, nw = nth >> 5;
+    const int Tp = (Tn + 3) & ~3;
     double bad = 0.0;
-    for (int j = 0; j < Tn; ++j) {
-        const int rows = Tn - j;
-        int lg = 0;
-        while (lg < 5 && (rows << (lg + 1)) <= nth) ++lg;
-        const int G = 1 << lg, lane = tid & (G - 1), sub = tid >> lg, nsub = nth >> lg;
-        const double* __restrict__ rowj = D + tri(j);
-        for (int i0 = j; i0 < Tn; i0 += nsub) {
-            const int i = i0 + sub;
-            const bool on = i < Tn;
-            double* __restrict__ rowi = D + tri(on ? i : j);
-            double di0 = 0.0, di1 = 0.0, dj0 = 0.0, dj1 = 0.0;
-            int k = lane;
-            for (; k + G < j; k += 2 * G) {
-                const double a0 = rowj[k], a1 = rowj[k + G], b0 = rowi[k], b1 = rowi[k + G];
-                di0 = fma(b0, a0, di0); dj0 = fma(a0, a0, dj0);
-                di1 = fma(b1, a1, di1); dj1 = fma(a1, a1, dj1);
-            }
-            if (k < j) { const double a0 = rowj[k]; di0 = fma(rowi[k], a0, di0); dj0 = fma(a0, a0, dj0); }
-            double di = di0 + di1, dj = dj0 + dj1;
-            for (int o = G >> 1; o > 0; o >>= 1) {
-                di += __shfl_xor_sync(0xffffffffu, di, o);
-                dj += __shfl_xor_sync(0xffffffffu, dj, o);
-            }
-            double pv = rowj[j] - dj;
-            if (!(pv > 0.0)) { bad = 1.0; pv = 1.0; }
-            const double inv = rsqrt(pv);
-            if (on && lane == 0) {
-                if (i == j) dinvT[j] = inv;
-                else rowi[j] = (rowi[j] - di) * inv;
+    for (int j0 = 0; j0 < Tp; j0 += 4) {
+        const double* d0 = D + tri(j0) + j0;
+        const double* d1 = D + tri(j0 + 1) + j0;
+        const double* d2 = D + tri(j0 + 2) + j0;
+        const double* d3 = D + tri(j0 + 3) + j0;
+        double a00 = d0[0], a10 = d1[0], a11 = d1[1], a20 = d2[0], a21 = d2[1], a22 = d2[2];
+        double a30 = d3[0], a31 = d3[1], a32 = d3[2], a33 = d3[3];
+        if (!(a00 > 0.0)) { bad = 1.0; a00 = 1.0; }
+        const double i0 = rsqrt(a00);
+        const double l10 = a10 * i0, l20 = a20 * i0, l30 = a30 * i0;
+        a11 = fma(-l10, l10, a11);
+        if (!(a11 > 0.0)) { bad = 1.0; a11 = 1.0; }
+        const double i1 = rsqrt(a11);
+        const double l21 = fma(-l20, l10, a21) * i1, l31 = fma(-l30, l10, a31) * i1;
+        a22 = fma(-l21, l21, fma(-l20, l20, a22));
+        if (!(a22 > 0.0)) { bad = 1.0; a22 = 1.0; }
+        const double i2 = rsqrt(a22);
+        const double l32 = fma(-l31, l21, fma(-l30, l20, a32)) * i2;
+        a33 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
+        if (!(a33 > 0.0)) { bad = 1.0; a33 = 1.0; }
+        const double i3 = rsqrt(a33);
+        for (int i = j0 + 4 + tid; i < Tp; i += nth) {
+            double* r = D + tri(i) + j0;
+            const double x0 = r[0] * i0;
+            const double x1 = fma(-x0, l10, r[1]) * i1;
+            const double x2 = fma(-x1, l21, fma(-x0, l20, r[2])) * i2;
+            const double x3 = fma(-x2, l32, fma(-x1, l31, fma(-x0, l30, r[3]))) * i3;
+            r[0] = x0; r[1] = x1; r[2] = x2; r[3] = x3;
+        }
+        __syncthreads();  // every thread has read the diagonal block; the panel rows are written
+        if (tid == 0) {
+            double* w1 = D + tri(j0 + 1) + j0;
+            double* w2 = D + tri(j0 + 2) + j0;
+            double* w3 = D + tri(j0 + 3) + j0;
+            w1[0] = l10; w2[0] = l20; w2[1] = l21; w3[0] = l30; w3[1] = l31; w3[2] = l32;
+            if (j0 < Tn) dinvT[j0] = i0;
+            if (j0 + 1 < Tn) dinvT[j0 + 1] = i1;
+            if (j0 + 2 < Tn) dinvT[j0 + 2] = i2;
+            if (j0 + 3 < Tn) dinvT[j0 + 3] = i3;
+        }
+        for (int i = j0 + 4 + wp; i < Tp; i += nw) {  // rank-4 update: a warp per row, a lane per column
+            double* __restrict__ row = D + tri(i);
+            const double xi0 = row[j0], xi1 = row[j0 + 1], xi2 = row[j0 + 2], xi3 = row[j0 + 3];
+            for (int k = j0 + 4 + lane; k <= i; k += 32) {
+                const double* xk = D + tri(k) + j0;
+                const double s = fma(xi3, xk[3], fma(xi2, xk[2], fma(xi1, xk[1], xi0 * xk[0])));
+                row[k] -= s;
             }
         }
         __syncthreads();

@@ -522,7 +522,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             int t = 0;
             // 96 columns: beyond that the dense factorisation of the (only ~40 % full) tail costs more than the
             // sparse levels it replaces (measured on the case118-shaped batch: T = 48 / 92 / 128 -> 79 / 61 / 67 ms)
-            while (t < 96 && (size_t)(t + 1) * (t + 2) / 2 + (size_t)((t + 2) & ~1) <= cap) ++t;
+            while (t < 96 && (size_t)(t + 4) * (t + 5) / 2 + (size_t)((t + 2) & ~1) <= cap) ++t;
             return t;
         };
         CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -658,7 +658,8 @@ static void place_arrays(const Prob& P, int phase, size_t budget_bytes, bool ipm
     if (ipm) {  // interior point: the dense tail of the factor (lives only here), then the solve scratch
         const CholDev& C = (phase == SQPQP_PHASE_FR) ? P.chol_fr : P.chol;
         if (C.T > 0) {
-            take(&pl->dtail, (size_t)C.T * (C.T + 1) / 2);
+            const size_t Tp = ((size_t)C.T + 3) & ~(size_t)3;  // dense_factor works in panels of 4 columns
+            take(&pl->dtail, Tp * (Tp + 1) / 2);
             take(&pl->dcol, C.T);
         }
         take(&pl->dinv, C.n);
