@@ -247,8 +247,9 @@ __device__ inline void dense_solve_warp(const double* __restrict__ D, const doub
 }
 
 // In-place numeric factorisation: the barrier phases of symbolic.hpp 4c (per sparse level the
-// diagonal entries, then the sub-diagonal entries; then the Schur complement of the dense tail), a
-// sub-warp per task.  Returns false (uniformly) if a pivot was not positive.
+// diagonal entries, then the sub-diagonal entries; then the Schur complement of the dense tail).  A
+// thread executes one SLOT per round: one lane's share of a task, the lane count chosen per task on
+// the host from its pair count.  Returns false (uniformly) if a pivot was not positive.
 template <class Team>
 __device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& pf) {
     double* L = W.L;
@@ -256,29 +257,32 @@ __device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& 
     int4 ph = C.fphase[0];
     for (int p = 0; p < C.nphase; ++p) {
         const int4 nxt = C.fphase[p + 1];  // (padded by one entry) off the critical path of the next phase
-        const int t0 = ph.x, nt = ph.y - ph.x, kind = ph.w;
-        const int lg = level_lg(T, nt), Ln = 1 << lg;
-        const int lane = T.tid() & (Ln - 1), sub = T.tid() >> lg, nsub = T.size() >> lg;
-        for (int r0 = 0; r0 < nt; r0 += nsub) {
-            const int t = r0 + sub;
-            const bool on = t < nt;
-            const int4 tk = C.ftask[t0 + (on ? t : 0)];
-            const int e = tk.x & 0x3fffffff;
-            const double k0 = (on && (tk.x >> 30)) ? L[e] : 0.0;
-            const double di = (on && kind == 1) ? W.dinv[tk.w] : 0.0;
-            double acc = on ? gather_dot(C.fp_ab, tk.y + lane, tk.z, Ln, L, L) : 0.0;
-            acc = subwarp_sum(acc, Ln);
-            if (on && lane == 0) {
+        const int s0 = ph.x, ns = ph.y - ph.x, kind = ph.w;
+        for (int r0 = 0; r0 < ns; r0 += T.size()) {
+            const int sidx = r0 + T.tid();
+            const bool on = sidx < ns;
+            const int4 sl = C.ftask[s0 + (on ? sidx : 0)];
+            const int e = sl.x & 0x3ffffff, Ln = 1 << ((sl.x >> 26) & 7);
+            const bool leader = on && ((sl.x >> 29) & 1);
+            const double k0 = (leader && (sl.x >> 30)) ? L[e] : 0.0;
+            const double di = (leader && kind == 1) ? W.dinv[sl.w] : 0.0;
+            double acc = on ? gather_dot(C.fp_ab, sl.y, sl.z, Ln, L, L) : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {  // lane groups of mixed (power of two, aligned) sizes share the butterfly
+                const double t = __shfl_xor_sync(0xffffffffu, acc, o);
+                if (o < Ln) acc += t;
+            }
+            if (leader) {
                 double v = k0 - acc;
                 if (kind == 0) {
                     if (!(v > 0.0)) { bad[0] = 1.0; v = 1.0; }
                     const double inv = rsqrt(v);
                     L[e] = v * inv;
-                    W.dinv[tk.w] = inv;
+                    W.dinv[sl.w] = inv;
                 } else if (kind == 1) {
                     L[e] = v * di;
                 } else {
-                    W.D[tk.w] = v;
+                    W.D[sl.w] = v;
                 }
             }
         }

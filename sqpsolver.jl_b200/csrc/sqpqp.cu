@@ -543,7 +543,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         }
         DALLOC(P.wJ, B * (size_t)(P.nnzJ > 0 ? P.nnzJ : 1));
         Symbolic Sy = symbolic_analyze(n, m, hJrb.data(), hJre.data(), hJc.data(), hHrp.data(), hHc.data(), 512, tail_cap(n));
-        if (Sy.ok && (int64_t)Sy.fp_ab.size() < ((int64_t)1 << 29)) {
+        if (Sy.ok && (int64_t)Sy.fp_ab.size() < ((int64_t)1 << 29) && Sy.nnzL < (1 << 26)) {
             int rc2 = upload_symbolic(Sy, P.chol, n);
             if (rc2) return rc2;
             DALLOC(P.Lval, B * (size_t)Sy.nnzL);
@@ -557,7 +557,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         P.has_chol_fr = 0;
         if (S > 0 && m > 0) {
             Symbolic Sf = symbolic_analyze(P.Ne, m, hJrb.data(), hJrb.data() + 1, hJc.data(), nullptr, nullptr, 512, tail_cap(P.Ne));
-            if (Sf.ok && (int64_t)Sf.fp_ab.size() < ((int64_t)1 << 29)) {
+            if (Sf.ok && (int64_t)Sf.fp_ab.size() < ((int64_t)1 << 29) && Sf.nnzL < (1 << 26)) {
                 int rc2 = upload_symbolic(Sf, P.chol_fr, P.Ne);
                 if (rc2) return rc2;
                 DALLOC(P.Lval_fr, B * (size_t)Sf.nnzL);

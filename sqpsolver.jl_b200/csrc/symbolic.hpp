@@ -36,12 +36,16 @@ struct Symbolic {
     std::vector<int> lev_ptr;            // [nlev+1] column range of each sparse level
     std::vector<int> fp_ptr;             // per entry id: range in fp_ab
     std::vector<int> fp_ab;              // interleaved pairs of L value indices to multiply-subtract
-    // factorisation as a list of barrier phases over flat task lists (4 ints each):
-    //   task  = (entry id | has_K << 30, first pair, end pair, aux)   aux: column (diag/offdiag) or packed tail position (Schur)
-    //   phase = (first task, end task, max pairs of a task, kind)     kind: 0 diagonal entries of a level, 1 sub-diagonal
+    // factorisation as a list of barrier phases over flat SLOT lists (4 ints each).  A task (one entry of L) gets
+    // 2^lg lanes, lg chosen from its pair count (<= 8 pairs per lane, widened when the phase is narrow); every lane
+    // of a task has its own slot, so a thread needs ONE coalesced 16-byte load to know its work:
+    //   slot  = (entry id | lg << 26 | leader << 29 | has_K << 30, first pair of this lane, end pair, aux)
+    //           the lane walks its pairs with stride 2^lg; aux: column (diag/offdiag) or packed tail position (Schur)
+    //   phase = (first slot, end slot, max pairs of a task, kind)     kind: 0 diagonal entries of a level, 1 sub-diagonal
     //           entries of a level, 2 Schur complement of the dense tail.   Tasks of a phase are sorted by pair count
-    //           (descending) so that the sub-warps of one round carry similar work.
+    //           (descending): lane groups are then aligned to their own (power of two) size inside a warp.
     std::vector<int> ftask, fphase;
+    int ftasks = 0;                      // number of tasks (entries) behind the slots
     // assembly: K_e = P[h] + sum_t wJ[a_t] * Jv[b_t]  (+ d[perm[j]] on the diagonal), wJ = w[row] .* Jv
     std::vector<int> atask_off;          // sourced sub-diagonal entries: (entry id, first term, end term, P value index | -1)
     std::vector<int> atask_diag;         // per column j: (entry id, first term, end term, P value index | -1)
@@ -269,12 +273,34 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
         struct Tk { int tgt, q0, q1, aux; };
         auto emit = [&](std::vector<Tk>& v, int kind) {
             std::stable_sort(v.begin(), v.end(), [](const Tk& a, const Tk& b) { return a.q1 - a.q0 > b.q1 - b.q0; });
-            int t0 = (int)S.ftask.size() / 4, mp = 0;
-            for (const Tk& t : v) {
-                S.ftask.push_back(t.tgt | (hasK[t.tgt] ? (1 << 30) : 0)); S.ftask.push_back(t.q0); S.ftask.push_back(t.q1); S.ftask.push_back(t.aux);
-                mp = std::max(mp, t.q1 - t.q0);
+            std::vector<int> lg(v.size(), 0);
+            long total = 0;
+            for (size_t t = 0; t < v.size(); ++t) {
+                int np = v[t].q1 - v[t].q0;
+                while (lg[t] < 5 && np > (8 << lg[t])) ++lg[t];
+                total += 1 << lg[t];
             }
-            S.fphase.push_back(t0); S.fphase.push_back(t0 + (int)v.size()); S.fphase.push_back(mp); S.fphase.push_back(kind);
+            // narrow phase: spread every task over more lanes while one round of a 512-thread team can hold them
+            while (total * 2 <= 512) {
+                bool any = false;
+                total = 0;
+                for (size_t t = 0; t < v.size(); ++t) {
+                    if (lg[t] < 5) { ++lg[t]; any = true; }
+                    total += 1 << lg[t];
+                }
+                if (!any) break;
+            }
+            int s0 = (int)S.ftask.size() / 4, mp = 0;
+            for (size_t t = 0; t < v.size(); ++t) {
+                const Tk& k = v[t];
+                for (int lane = 0; lane < (1 << lg[t]); ++lane) {
+                    S.ftask.push_back(k.tgt | (lg[t] << 26) | (lane == 0 ? (1 << 29) : 0) | (hasK[k.tgt] ? (1 << 30) : 0));
+                    S.ftask.push_back(k.q0 + lane); S.ftask.push_back(k.q1); S.ftask.push_back(k.aux);
+                }
+                mp = std::max(mp, k.q1 - k.q0);
+            }
+            S.ftasks += (int)v.size();
+            S.fphase.push_back(s0); S.fphase.push_back((int)S.ftask.size() / 4); S.fphase.push_back(mp); S.fphase.push_back(kind);
             v.clear();
         };
         std::vector<Tk> v;

@@ -18,6 +18,7 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
     if (!S.ok) return -1;
     const int n0 = S.n0, T = S.T;
     std::vector<double> L(S.nnzL, std::nan("")), D((size_t)tri(T) + T, 0.0), dinv(n), wJ(S.jrow.size());
+    if (S.nnzL >= (1 << 26)) return -9;  // slot encoding: 26 bits of entry id
     // assembly (chol_assemble): wJ, then the diagonal and the sourced sub-diagonal entries; pure fill stays unset (NaN here:
     // a factor task that read it although has_K = 0 would poison the result)
     for (size_t a = 0; a < S.jrow.size(); ++a) wJ[a] = S.jrow[a] >= 0 ? w[S.jrow[a]] * Jv[a] : 0.0;
@@ -33,13 +34,20 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
     // factorisation phases (chol_factor)
     for (size_t p = 0; p < S.fphase.size() / 4; ++p) {
         const int* ph = &S.fphase[4 * p];
-        for (int t = ph[0]; t < ph[1]; ++t) {
+        for (int t = ph[0]; t < ph[1];) {
             const int* tk = &S.ftask[4 * (size_t)t];
-            const int e = tk[0] & 0x3fffffff;
+            const int e = tk[0] & 0x3ffffff, Ln = 1 << ((tk[0] >> 26) & 7);
+            if (!((tk[0] >> 29) & 1)) return -6;                // a task starts with its leader slot
+            if ((t - ph[0]) % Ln != 0) return -7;               // lane groups aligned to their size
             double acc = 0.0;
-            if (tk[2] - tk[1] > ph[2]) return -5;
-            for (int q = tk[1]; q < tk[2]; ++q) acc += L[S.fp_ab[2 * (size_t)q]] * L[S.fp_ab[2 * (size_t)q + 1]];
-            double v = ((tk[0] >> 30) ? L[e] : 0.0) - acc;
+            int npairs = 0;
+            for (int lane = 0; lane < Ln; ++lane) {             // the lanes of the task, each with stride Ln
+                const int* sl = &S.ftask[4 * (size_t)(t + lane)];
+                if ((sl[0] & 0x3ffffff) != e || sl[1] != tk[1] + lane || (lane > 0 && ((sl[0] >> 29) & 1))) return -8;
+                for (int q = sl[1]; q < sl[2]; q += Ln, ++npairs) acc += L[S.fp_ab[2 * (size_t)q]] * L[S.fp_ab[2 * (size_t)q + 1]];
+            }
+            if (npairs != tk[2] - tk[1] || npairs > ph[2]) return -5;
+            double v = ((tk[0] >> 30) & 1 ? L[e] : 0.0) - acc;
             if (ph[3] == 0) {
                 if (!(v > 0.0)) return -2;
                 double inv = 1.0 / std::sqrt(v);
@@ -50,6 +58,7 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
             } else {
                 D[tk[3]] = v;
             }
+            t += Ln;
         }
     }
     if (S.nlev > 0 && S.lev_ptr[S.nlev] != n0) return -3;
