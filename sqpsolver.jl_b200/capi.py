@@ -82,7 +82,7 @@ EXPORTS = [
     "sqpqp_setup_nlp", "sqpqp_update_nlp", "sqpqp_update_nlp_device", "sqpqp_solve_tr", "sqpqp_num_slacks",
     "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
     "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
-    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device",
+    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read",
 ]
 
 
@@ -139,6 +139,7 @@ def lib():
     L.sqpqp_chol_stats.argtypes = [vp, _lp, _lp, _lp]
     L.sqpqp_chol_layout.argtypes = [vp, _lp, _lp]
     L.sqpqp_prof_read.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.sqpqp_debug_read.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_int64]
     L.sqpqp_spmv.argtypes = [vp, C.c_int32, _dp, _dp]
     L.sqpqp_spmv_device.argtypes = [vp, C.c_int32, vp, vp]
     L.sqpqp_num_slacks.argtypes = [vp, _ip]
@@ -300,6 +301,12 @@ class Engine:
 
     def spmv_device(self, which, x_dev_ptr, y_dev_ptr):
         self._ck(self.L.sqpqp_spmv_device(self.h, which, C.c_void_p(int(x_dev_ptr)), C.c_void_p(int(y_dev_ptr))))
+
+    def debug_read(self, kind, idx=0, b=0, count=None):
+        count = int(count if count is not None else max(self.n + self.S, self.m, 1) * 64)
+        out = np.full(count, np.nan)
+        self._ck(self.L.sqpqp_debug_read(self.h, kind, idx, b, _d(out), count))
+        return out
 
     def prof_read(self):
         """Cycles per solve segment (csrc/common.cuh ProfSeg) since the last call; zeros in a normal build."""

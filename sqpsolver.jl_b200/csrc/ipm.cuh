@@ -225,13 +225,16 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         // Termination (Ipopt-style scaling): primal residual relative to |x|,|Ax|; stationarity relative to
         // the gradient terms (its attainable floor is ~1e-9 of them, the conditioning of K); complementarity
         // (largest s*z, unscaled) absolute unless the multipliers themselves are large.
+        // The start-point projection (LP phase) is solved once per SQP run and its solution IS the first iterate:
+        // weakly active bounds are only located to sqrt(s*z), so its complementarity target is 1000x tighter.
         const double comp_u = mx[6] / c, sc = fmax(1.0, ymx / c / 100.0);
-        if (out.rp <= o.ipm_eps * scale_p && out.rd <= o.ipm_eps * scale_d && comp_u <= o.ipm_eps * sc) {
+        const double eps_c = (phase == SQPQP_PHASE_LP) ? 1e-3 * o.ipm_eps : o.ipm_eps;
+        if (out.rp <= o.ipm_eps * scale_p && out.rd <= o.ipm_eps * scale_d && comp_u <= eps_c * sc) {
             out.solved = true;
             break;
         }
         const double acc_eps = 100.0 * o.ipm_eps;
-        bool acceptable = out.rp <= acc_eps * scale_p && out.rd <= acc_eps * scale_d && comp_u <= acc_eps * sc;
+        bool acceptable = out.rp <= acc_eps * scale_p && out.rd <= acc_eps * scale_d && comp_u <= 100.0 * eps_c * sc;
         acc_cnt = acceptable ? acc_cnt + 1 : 0;
         out.almost = out.rp <= 1e-6 * scale_p && out.rd <= 1e-6 * scale_d && comp_u <= 1e-6 * sc;
         if (acc_cnt >= 8) {  // stuck on the floor of an acceptable point

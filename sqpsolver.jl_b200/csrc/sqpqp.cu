@@ -330,6 +330,28 @@ extern "C" int sqpqp_prof_read(sqpqp_handle h, uint64_t* out32) {
     return 0;
 }
 
+// Development aid: copy one per-instance work array of instance b back to the host.
+// kind 0: N-vector slot idx, 1: M-vector slot idx, 2: factor values, 3: solve scratch, 4: inverse diagonal, 5: wJ.
+extern "C" int sqpqp_debug_read(sqpqp_handle h, int32_t kind, int32_t idx, int32_t b, double* out, int64_t count) {
+    if (!h || !out) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    const double* src = nullptr;
+    size_t len = 0;
+    if (kind == 0 && idx >= 0 && idx < N_COUNT) { src = P.nv[idx] + (size_t)b * P.Ne; len = P.Ne; }
+    else if (kind == 1 && idx >= 0 && idx < M_COUNT) { src = P.mv[idx] + (size_t)b * P.m; len = P.m; }
+    else if (kind == 2 && P.has_chol) { src = P.Lval + (size_t)b * P.chol.nnzL; len = P.chol.nnzL; }
+    else if (kind == 3 && P.has_chol) { src = P.yw + (size_t)b * P.n; len = P.n; }
+    else if (kind == 4 && P.has_chol) { src = P.dinv + (size_t)b * P.n; len = P.n; }
+    else if (kind == 5 && P.has_chol) { src = P.wJ + (size_t)b * P.nnzJ; len = P.nnzJ; }
+    else return fail(h, SQPQP_E_BADARG, "bad selector");
+    if ((size_t)count < len) len = (size_t)count;
+    CUDA_OK(cudaMemcpy(out, src, len * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" int sqpqp_chol_layout(sqpqp_handle h, int64_t* tail_cols, int64_t* tree_levels) {
     if (!h) return SQPQP_E_BADARG;
     if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
@@ -486,7 +508,11 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             int rc2 = dalloc(h, &d, v.size());
             if (rc2) return rc2;
             if (!v.empty()) {
-                cudaError_t e2 = cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice);
+                // on the engine's own stream and waited for: the stream is non-blocking, so it does NOT order after
+                // the legacy default stream a plain cudaMemcpy from pageable memory finishes its DMA on -- with the
+                // 300 MB programs of a 2000-bus instance the first solve used to start on half-uploaded indices
+                cudaError_t e2 = cudaMemcpyAsync(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+                if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(h->stream);
                 if (e2 != cudaSuccess) return fail_cuda(h, e2, "cudaMemcpy symbolic", __LINE__);
             }
             *dst = d;

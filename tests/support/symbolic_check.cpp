@@ -31,7 +31,9 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
     if ((int)S.atask_diag.size() != 4 * n) return -4;
     for (int j = 0; j < n; ++j) assemble(&S.atask_diag[4 * (size_t)j], true, j);
     for (size_t t = 0; t < S.atask_off.size() / 4; ++t) assemble(&S.atask_off[4 * t], false, 0);
-    // factorisation phases (chol_factor)
+    // factorisation phases (chol_factor).  done[e] = phase that produced entry e: a task may only read entries of
+    // EARLIER phases (the device runs the tasks of one phase concurrently).
+    std::vector<int> done(S.nnzL, 1 << 30), ddone(n, 1 << 30);
     for (size_t p = 0; p < S.fphase.size() / 4; ++p) {
         const int* ph = &S.fphase[4 * p];
         for (int t = ph[0]; t < ph[1];) {
@@ -44,7 +46,11 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
             for (int lane = 0; lane < Ln; ++lane) {             // the lanes of the task, each with stride Ln
                 const int* sl = &S.ftask[4 * (size_t)(t + lane)];
                 if ((sl[0] & 0x3ffffff) != e || sl[1] != tk[1] + lane || (lane > 0 && ((sl[0] >> 29) & 1))) return -8;
-                for (int q = sl[1]; q < sl[2]; q += Ln, ++npairs) acc += L[S.fp_ab[2 * (size_t)q]] * L[S.fp_ab[2 * (size_t)q + 1]];
+                for (int q = sl[1]; q < sl[2]; q += Ln, ++npairs) {
+                    const int ea = S.fp_ab[2 * (size_t)q], eb = S.fp_ab[2 * (size_t)q + 1];
+                    if (done[ea] >= (int)p || done[eb] >= (int)p) return -10;  // intra-phase dependency
+                    acc += L[ea] * L[eb];
+                }
             }
             if (npairs != tk[2] - tk[1] || npairs > ph[2]) return -5;
             double v = ((tk[0] >> 30) & 1 ? L[e] : 0.0) - acc;
@@ -53,11 +59,14 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
                 double inv = 1.0 / std::sqrt(v);
                 L[e] = v * inv;
                 dinv[tk[3]] = inv;
+                ddone[tk[3]] = (int)p;
             } else if (ph[3] == 1) {
+                if (ddone[tk[3]] >= (int)p) return -11;
                 L[e] = v * dinv[tk[3]];
             } else {
                 D[tk[3]] = v;
             }
+            done[e] = (int)p;
             t += Ln;
         }
     }
