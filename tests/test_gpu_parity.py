@@ -327,6 +327,58 @@ def test_batched_spmv_bit_exact_against_sequential_csr(engine, make):
         assert np.abs(engine.spmv(which, xs[which])[0] - yref).max() <= 1e-12 * max(1.0, np.abs(yref).max())
 
 
+def test_case2000_start_projection_and_first_subproblems(built_lib):
+    """BASELINE configs[3]: the ~2000-bus synthetic network, one instance on one GPU (cooperative-grid team, 668-level
+    sparse Cholesky).  The start-point projection (subproblem_JuMP.jl:185-244) must agree with the oracle's, the first
+    QP must be classified infeasible like the oracle's (it drives the loop into feasibility restoration,
+    sqp_trust_region.jl:151-168) and the restoration LP must reach the oracle's optimal violation."""
+    from oracle.subproblem import sub_optimize_lp
+    nlp = AcopfPolar(synth_net(2000, 3000, 400, 2000))
+    x0 = np.asarray(nlp.x0, dtype=float)
+    X = x0[None, :]
+    dE = np.zeros((1, nlp.nnz_jac_coo)); nlp.eval_jac_g(X, dE)
+    eng = capi.Engine(0)
+    try:
+        _setup(eng, nlp)
+        assert eng.chol_stats()["nnzL"] > 300_000
+        E = np.zeros((1, nlp.m)); nlp.eval_g(X, E)
+        df = np.zeros((1, nlp.n)); nlp.eval_grad_f(X, df)
+        hv = np.zeros((1, nlp.nnz_hess_coo)); nlp.eval_h(X, 1.0, np.zeros((1, nlp.m)), hv)
+        eng.update_nlp(dE, hv, df, E)
+        p, lam, mxL, mxU, sl, st, info = eng.solve_tr(capi.PHASE_LP, X, np.full(1, np.inf))
+        assert st[0] in OK and info[0]["admm_iters"] == 0 and info[0]["ipm_iters"] < 40
+        J = CooMatrix(nlp.j_row, nlp.j_col, nlp.m, nlp.n); J.fill(dE[0])
+        xo, _, _, _, so = sub_optimize_lp(J.to_scipy(), nlp.g_L, nlp.g_U, nlp.x_L, nlp.x_U, x0, nlp.num_linear_constraints, nlp.m)
+        assert so in qs.OK_STATUSES
+        fo, fd = ((xo - x0) ** 2).sum(), ((p[0] - x0) ** 2).sum()
+        assert abs(fd - fo) <= 1e-8 * max(1.0, fo)                      # same optimal distance
+        assert np.abs(p[0] - xo).max() <= 2e-5                         # weakly active bounds: located to sqrt(s z) by both
+        # first QP at the projected point: infeasible on both sides
+        X1 = xo[None, :]
+        nlp.eval_jac_g(X1, dE); nlp.eval_g(X1, E); nlp.eval_grad_f(X1, df); nlp.eval_h(X1, 1.0, np.zeros((1, nlp.m)), hv)
+        eng.update_nlp(dE, hv, df, E)
+        out = eng.solve_tr(capi.PHASE_QP, X1, np.full(1, 10.0))
+        assert out[5][0] in (capi.MOI_LOCALLY_INFEASIBLE, capi.MOI_INFEASIBLE)
+        assert not out[0].any() and not out[1].any()                   # zero-filled like collect_solution! (:551-555)
+        # feasibility restoration: sum of slacks at the optimum vs the oracle's
+        out = eng.solve_tr(capi.PHASE_FR, X1, np.full(1, 10.0))
+        assert out[5][0] in OK
+        viol_dev = float(out[4][0].sum())
+        J.fill(dE[0])
+        H = SymCooMatrix(nlp.h_row, nlp.h_col, nlp.n); H.fill(hv[0])
+        from oracle.subproblem import QpData, QpOracle
+        data = QpData(H.to_scipy(), df[0], J.to_scipy(), E[0], nlp.g_L, nlp.g_U, nlp.x_L, nlp.x_U, nlp.num_linear_constraints)
+        ora = QpOracle(data)
+        ora.create_model(10.0)
+        ro = ora.sub_optimize(xo, 10.0)
+        assert ro[-1] in qs.INFEASIBLE_STATUSES
+        rf = ora.sub_optimize_FR(xo, 10.0)
+        viol_ora = float(sum(np.sum(v) for v in rf[4].values()))
+        assert abs(viol_dev - viol_ora) <= 1e-6 * max(1.0, viol_ora), (viol_dev, viol_ora)
+    finally:
+        eng.close()
+
+
 def test_solve_is_bit_reproducible(engine):
     """Deterministic reductions: two cold solves of the same QP give identical bits."""
     g = np.load(os.path.join(GOLD, "case9_mu1e4.npz"))
