@@ -197,9 +197,28 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
                           double c, int phase, const double* xk_scaled_start);
 
 // ---------------------------------------------------------------------------------------
-template <class Team>
+// MODE 0: interior point, then the ADMM fallback in the same kernel (cooperative-grid team).
+// MODE 1: interior point only; an instance it cannot finish is flagged in P.fb_flag for the MODE 2 launch that follows.
+// MODE 2: ADMM only, for the flagged instances (or all of them when options.method == 1).
+// CTA teams use 1 + 2: the interior-point kernel then carries no ADMM / polish state, which is what keeps the
+// 64-register build from spilling (the spill traffic of the monolithic kernel was the larger part of its DRAM traffic,
+// profiles/r01_ncu_summary_v2.md).  The work-vector aliases below are scoped per stage for the same reason.
+#define SQPQP_ALIASES \
+    double *q = I.nv[N_Q], *xl = I.nv[N_XL], *xu = I.nv[N_XU], *D = I.nv[N_D], *x = I.nv[N_X], *zb = I.nv[N_ZB], \
+           *yb = I.nv[N_YB], *rb = I.nv[N_RB], *xt = I.nv[N_XT], *rv = I.nv[N_R], *dsh = I.nv[N_DSH], \
+           *hd = I.nv[N_HD], *tmpN = I.nv[N_TMP], *tmpN2 = I.nv[N_TMP2], *xw = I.nv[N_XW], *ybw = I.nv[N_YBW]; \
+    double *rl = I.mv[M_RL], *ru = I.mv[M_RU], *Es = I.mv[M_ES], *zc = I.mv[M_ZC], *yc = I.mv[M_YC], *rc = I.mv[M_RC], \
+           *tmpM = I.mv[M_TMP], *Ax = I.mv[M_AX], *ycw = I.mv[M_YCW]; \
+    (void)q; (void)xl; (void)xu; (void)D; (void)x; (void)zb; (void)yb; (void)rb; (void)xt; (void)rv; (void)dsh; (void)hd; \
+    (void)tmpN; (void)tmpN2; (void)xw; (void)ybw; (void)rl; (void)ru; (void)Es; (void)zc; (void)yc; (void)rc; (void)tmpM; \
+    (void)Ax; (void)ycw;
+
+template <int MODE, class Team>
 __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, int inst, int phase,
                                const Placement* pl, double* dsm) {
+    if constexpr (MODE == 2) {
+        if (o.method != 1 && P.fb_flag[inst] == 0) return;  // uniform per team: solved by the interior-point launch
+    }
     Prof pfo;
     pfo.start();
     Inst I;
@@ -236,12 +255,9 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     const double* xk = P.xk + (size_t)inst * n;
     const double delta = P.delta[inst];
 
-    double *q = I.nv[N_Q], *xl = I.nv[N_XL], *xu = I.nv[N_XU], *D = I.nv[N_D], *x = I.nv[N_X], *zb = I.nv[N_ZB],
-           *yb = I.nv[N_YB], *rb = I.nv[N_RB], *xt = I.nv[N_XT], *rv = I.nv[N_R], *dsh = I.nv[N_DSH],
-           *hd = I.nv[N_HD], *tmpN = I.nv[N_TMP], *tmpN2 = I.nv[N_TMP2], *xw = I.nv[N_XW], *ybw = I.nv[N_YBW];
-    double *rl = I.mv[M_RL], *ru = I.mv[M_RU], *Es = I.mv[M_ES], *zc = I.mv[M_ZC], *yc = I.mv[M_YC], *rc = I.mv[M_RC],
-           *tmpM = I.mv[M_TMP], *Ax = I.mv[M_AX], *ycw = I.mv[M_YCW];
-
+    double c = 1.0;
+    {   // ================= stage A: QP data, equilibration (its aliases die with the block) =================
+    SQPQP_ALIASES
     // ---- 0. assemble the unscaled QP (set_trust_region!, modify_constraints!) ----------
     for_n(T, N, [&](int j) {
         double lo, hi, qq;
@@ -278,7 +294,6 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     // ---- 1. Ruiz equilibration (D cols, Es rows, c cost) --------------------------------
     for_n(T, N, [&](int j) { D[j] = 1.0; });
     for_n(T, M, [&](int i) { Es[i] = 1.0; });
-    double c = 1.0;
     T.sync();
     for (int it = 0; it < o.ruiz_iters; ++it) {
         // column norms (rows of the symmetric P and of the transpose)
@@ -339,6 +354,7 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     }
     for_n(T, M, [&](int i) { rl[i] *= Es[i]; ru[i] *= Es[i]; });
     T.sync();
+    }   // stage A
 
     int status = SQPQP_MOI_ITERATION_LIMIT;
     int k = 0, cg_total = 0, polish_tries = 0, polish_cg = 0, rho_updates = 0, checks = 0, bumps = 0;
@@ -350,7 +366,12 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     // ---- 1b. interior point method (default where the symbolic Cholesky is available) ---------
     bool ipm_done = false, ipm_blowup = false;
     const bool fr = phase == SQPQP_PHASE_FR;
-    if ((fr ? P.has_chol_fr : P.has_chol) && o.method != 1) {
+    if constexpr (MODE == 2) {  // statistics of the interior-point launch that flagged this instance
+        ipm_iters = P.o_info[inst].ipm_iters;
+        nfact = P.o_info[inst].chol_factorizations;
+        ipm_blowup = P.fb_flag[inst] == 2;
+    }
+    if (MODE != 2 && (fr ? P.has_chol_fr : P.has_chol) && o.method != 1) {
         const CholDev& CD = fr ? P.chol_fr : P.chol;
         CholWork W;
         W.L = fr ? P.Lval_fr + (size_t)inst * CD.nnzL : P.Lval + (size_t)inst * CD.nnzL;
@@ -366,6 +387,7 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
         }
         const double* start = nullptr;
         if (phase == SQPQP_PHASE_LP) {
+            double *x = I.nv[N_X], *D = I.nv[N_D];
             for_n(T, N, [&](int j) { x[j] = xk[j] / D[j]; });
             T.sync();
             start = x;
@@ -387,7 +409,18 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
             rb_floor = io.rho_p;
         }
     }
-    if (!ipm_done && o.method != 2) {
+    if constexpr (MODE == 1) {
+        if (T.tid() == 0) P.fb_flag[inst] = (!ipm_done && o.method != 2) ? (ipm_blowup ? 2 : 1) : 0;
+        if (!ipm_done && o.method != 2) {  // handed to the ADMM launch; keep the interior-point statistics for it
+            if (T.tid() == 0) {
+                P.o_info[inst].ipm_iters = ipm_iters;
+                P.o_info[inst].chol_factorizations = nfact;
+            }
+            return;
+        }
+    }
+    if (MODE != 1 && !ipm_done && o.method != 2) {
+    SQPQP_ALIASES
     // ---- 2. nonconvexity guard: lambda_min(Ps) by power iteration on (bound I - Ps) -------
     if (I.useH) {
         double bnd[1] = {0.0};
@@ -712,6 +745,7 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     else if (!ipm_done) status = SQPQP_MOI_NUMERICAL_ERROR;
 
     // ---- 5. outputs (collect_solution!, subproblem_JuMP.jl:514-563) -----------------------
+    SQPQP_ALIASES
     bool okst = (status == SQPQP_MOI_LOCALLY_SOLVED || status == SQPQP_MOI_ALMOST_LOCALLY_SOLVED ||
                  status == SQPQP_MOI_ITERATION_LIMIT);
     double obj[1] = {0.0};
@@ -771,7 +805,7 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
 // MAXT threads per CTA, at least MINB CTAs per SM: <512,1> keeps 128 registers/thread for the
 // one-CTA-per-SM resident configuration; <256,4> and <128,8> cap registers at 64 so that many
 // instances share an SM and hide each other's (L2-latency-bound) level-scheduled phases.
-template <int MAXT, int MINB>
+template <int MAXT, int MINB, int MODE>
 __global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(const __grid_constant__ Prob P, const __grid_constant__ DevOpts O, int phase,
                                                           const __grid_constant__ Placement pl) {
     __shared__ double sh[2 * SQPQP_MAX_RED * 32];
@@ -779,7 +813,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(const __grid_constant_
     for (int inst = blockIdx.x; inst < P.batch; inst += gridDim.x) {
         if (P.active && !P.active[inst]) continue;
         CtaTeam T(sh);
-        solve_instance(T, P, O.o, inst, phase, &pl, dsm);
+        solve_instance<MODE>(T, P, O.o, inst, phase, &pl, dsm);
         __syncthreads();
     }
 }
@@ -789,6 +823,6 @@ __global__ void __launch_bounds__(256) k_solve_grid(const __grid_constant__ Prob
     GridTeam T(sh, P.gred, P.gred_stride);
     for (int inst = 0; inst < P.batch; ++inst) {
         if (P.active && !P.active[inst]) continue;
-        solve_instance(T, P, O.o, inst, phase, (const Placement*)nullptr, (double*)nullptr);
+        solve_instance<0>(T, P, O.o, inst, phase, (const Placement*)nullptr, (double*)nullptr);
     }
 }

@@ -93,6 +93,7 @@ struct Prob {
     // outputs
     double *o_p, *o_lam, *o_mxL, *o_mxU, *o_slack;
     sqpqp_info* o_info;
+    int* fb_flag;                // [batch] 0 solved by the interior-point launch, 1 needs the ADMM launch, 2 ditto after a blow-up
     // interior-point path: symbolic Cholesky (null n = unavailable), per-instance factor values
     // [batch][nnzL] and permuted solve scratch [batch][n]
     CholDev chol;      // QP / SOC / LP-projection phases: n columns, P = H or 2I

@@ -245,9 +245,7 @@ extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     h->max_dyn_smem = optin - 4096 - 1024;  // static reduction scratch + slack
     if (h->max_dyn_smem < 0) h->max_dyn_smem = 0;
-    cudaFuncSetAttribute(k_solve_cta<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
-    cudaFuncSetAttribute(k_solve_cta<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
-    {   // four CTAs per SM: (SM shared memory - 4 x (static scratch + 1 KB system reservation)) / 4
+    {   // shared memory per CTA: four / two CTAs per SM = (SM shared memory - n x (static scratch + 1 KB system reservation)) / n
         int per_sm = 0;
         cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
         int v = (per_sm / 4 - 4096 - 1024) & ~1023;
@@ -255,10 +253,12 @@ extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
         v = (per_sm / 2 - 4096 - 1024) & ~1023;
         h->cta2_smem = v < 32 * 1024 ? 32 * 1024 : v;
     }
-    cudaFuncSetAttribute(k_solve_cta<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta4_smem);
-    cudaFuncSetAttribute(k_solve_cta<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta4_smem);
-    cudaFuncSetAttribute(k_solve_cta<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta2_smem);
-    cudaFuncSetAttribute(k_solve_cta<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024);
+    cudaFuncSetAttribute(k_solve_cta<512, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
+    cudaFuncSetAttribute(k_solve_cta<512, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
+    cudaFuncSetAttribute(k_solve_cta<512, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta2_smem);
+    cudaFuncSetAttribute(k_solve_cta<512, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta2_smem);
+    cudaFuncSetAttribute(k_solve_cta<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta4_smem);
+    cudaFuncSetAttribute(k_solve_cta<256, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta4_smem);
     *out = h;
     return 0;
 }
@@ -300,7 +300,7 @@ extern "C" double sqpqp_last_solve_ms(sqpqp_handle h) {
 
 extern "C" int sqpqp_set_options(sqpqp_handle h, const sqpqp_options* o) {
     if (!h || !o) return SQPQP_E_BADARG;
-    if (o->threads < 0 || o->threads > 1024 || (o->threads % 32) != 0) return fail(h, SQPQP_E_BADARG, "threads must be a multiple of 32 in [0,1024]");
+    if (o->threads < 0 || o->threads > 512 || (o->threads % 32) != 0) return fail(h, SQPQP_E_BADARG, "threads must be a multiple of 32 in [0,512]");
     if (o->check_every < 1 || o->max_iter < 1 || !(o->rho0 > 0) || !(o->alpha > 0 && o->alpha < 2)) return fail(h, SQPQP_E_BADARG, "bad option value");
     h->opts = *o;
     return 0;
@@ -478,6 +478,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
     DALLOC(P.o_p, B * n); DALLOC(P.o_lam, B * (m > 0 ? m : 1)); DALLOC(P.o_mxL, B * n); DALLOC(P.o_mxU, B * n);
     DALLOC(P.o_slack, B * (S > 0 ? S : 1));
     DALLOC(P.o_info, B);
+    DALLOC(P.fb_flag, B);
     DALLOC(h->d_dE, B * (size_t)nnz_j); DALLOC(h->d_hval, B * (size_t)nnz_h); DALLOC(h->d_df, B * n); DALLOC(h->d_E, B * (m > 0 ? m : 1));
     DALLOC(h->d_xk, B * n); DALLOC(h->d_delta, B); DALLOC(h->d_Eov, B * (m > 0 ? m : 1)); DALLOC(h->d_active, B);
     const size_t nb = bounds_per_instance ? B : 1;
@@ -766,12 +767,28 @@ static int launch_solve(sqpqp_handle h, int phase) {
         }
         if (ipm && CD.T > 0 && pl.dtail < 0) return fail(h, SQPQP_E_STATE, "dense tail of the factor does not fit the shared-memory budget of this launch configuration");
         size_t dyn = (size_t)pl.total * sizeof(double);
-        if (occ >= 8 && threads <= 128) k_solve_cta<128, 8><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
-        else if (occ >= 4 && threads <= 256) k_solve_cta<256, 4><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
-        else if (occ == 3 && threads <= 256) k_solve_cta<256, 3><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
-        else if (occ >= 2 && threads <= 512) k_solve_cta<512, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
-        else if (threads > 512) k_solve_cta<1024, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
-        else k_solve_cta<512, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+        // interior-point launch, then the ADMM launch for the instances it flagged (a no-op for the others); with
+        // options.method == 1 only the ADMM launch (all instances), with method == 2 only the interior-point one
+        const int cfg = (occ >= 3 && threads <= 256) ? 4 : (occ >= 2 ? 2 : 1);
+        auto launch = [&](int mode) {
+            if (cfg == 4) {
+                if (mode == 1) k_solve_cta<256, 4, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+                else k_solve_cta<256, 4, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+            } else if (cfg == 2) {
+                if (mode == 1) k_solve_cta<512, 2, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+                else k_solve_cta<512, 2, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+            } else {
+                if (mode == 1) k_solve_cta<512, 1, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+                else k_solve_cta<512, 1, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+            }
+            h->launches++;
+        };
+        if (threads > 512) threads = 512;
+        if (cfg == 4 && threads > 256) threads = 256;
+        if (ipm) launch(1);
+        else CUDA_OK(cudaMemsetAsync(P.fb_flag, 0, B * sizeof(int), h->stream));
+        if (h->opts.method != 2) launch(2);
+        h->launches--;  // counted below
     }
     h->launches++;
     CUDA_OK(cudaEventRecord(h->ev1, h->stream));
