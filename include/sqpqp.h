@@ -184,6 +184,15 @@ int sqpqp_num_slacks(sqpqp_handle h, int32_t* S);
 int sqpqp_merit(sqpqp_handle h, const double* x, const double* p, const double* E_trial, const double* f_trial,
                 const double* mu, const int32_t* fr,
                 double* viol0, double* viol_trial, double* phi_trial, double* q0, double* qk);
+/* Line-search primitives on the current device matrices (the reference's line-search driver, sqp_line_search.jl, is not
+ * compiled by the reference -- sqp.jl:226 -- these are the device quantities its merit maths needs: compute_mu_rule2!
+ * :280-291, compute_alpha :303-334, compute_phi sqp.jl:170-183, compute_derivative sqp.jl:190-213 + merit.jl:13-17,
+ * norm_complementarity common.jl:30-47).  Inputs per instance: x[n], p[n], alpha, E_trial[m] = g(x + alpha p),
+ * mu_rows[m], lambda[m].  out8 is [8][batch]:
+ *   0 df'p   1 p'Hp   2 |viol(E,x)|_1   3 |viol(E,x)|_inf   4 sum_i mu_i viol_i(E) + |mu|_inf sum_j viol_j(x)
+ *   5 the same at (E_trial, x + alpha p)   6 |viol(E_trial, x + alpha p)|_1   7 norm_complementarity(E, lambda), p = Inf. */
+int sqpqp_linesearch_terms(sqpqp_handle h, const double* x, const double* p, const double* alpha, const double* E_trial,
+                           const double* mu_rows, const double* lambda, double* out8);
 /* KT_residuals (common.jl:14-23) as coded, per instance. */
 int sqpqp_kt_residuals(sqpqp_handle h, const double* lambda, const double* mult_x_U, const double* mult_x_L,
                        double* kt);

@@ -82,7 +82,7 @@ EXPORTS = [
     "sqpqp_setup_nlp", "sqpqp_update_nlp", "sqpqp_update_nlp_device", "sqpqp_solve_tr", "sqpqp_num_slacks",
     "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
     "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
-    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read",
+    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read", "sqpqp_linesearch_terms",
 ]
 
 
@@ -139,6 +139,7 @@ def lib():
     L.sqpqp_chol_stats.argtypes = [vp, _lp, _lp, _lp]
     L.sqpqp_chol_layout.argtypes = [vp, _lp, _lp]
     L.sqpqp_prof_read.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.sqpqp_linesearch_terms.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
     L.sqpqp_debug_read.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_int64]
     L.sqpqp_spmv.argtypes = [vp, C.c_int32, _dp, _dp]
     L.sqpqp_spmv_device.argtypes = [vp, C.c_int32, vp, vp]
@@ -338,6 +339,17 @@ class Engine:
         kt = np.zeros(B)
         self._ck(self.L.sqpqp_kt_residuals(self.h, _d(lam), _d(mxU), _d(mxL), _d(kt)))
         return kt
+
+    def linesearch_terms(self, x, p, alpha, E_trial, mu_rows, lam):
+        """Device line-search primitives (include/sqpqp.h: sqpqp_linesearch_terms); returns a dict of [batch] arrays."""
+        B, n, m = self.batch, self.n, self.m
+        x = _f64(x).reshape(B, n); p = _f64(p).reshape(B, n)
+        alpha = np.ascontiguousarray(np.broadcast_to(np.asarray(alpha, dtype=np.float64), (B,)))
+        E_trial = _f64(E_trial).reshape(B, m); mu_rows = _f64(mu_rows).reshape(B, m); lam = _f64(lam).reshape(B, m)
+        out = np.zeros((8, B))
+        self._ck(self.L.sqpqp_linesearch_terms(self.h, _d(x), _d(p), _d(alpha), _d(E_trial), _d(mu_rows), _d(lam), _d(out)))
+        keys = ("dfp", "pHp", "viol1", "violinf", "wviol0", "wviol_trial", "viol1_trial", "compl")
+        return {k: out[i] for i, k in enumerate(keys)}
 
     def jac_times(self, p):
         p = _f64(p).reshape(self.batch, self.n)

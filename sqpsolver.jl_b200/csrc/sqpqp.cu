@@ -920,6 +920,33 @@ extern "C" int sqpqp_merit(sqpqp_handle h, const double* x, const double* p, con
     return finish(h);
 }
 
+extern "C" int sqpqp_linesearch_terms(sqpqp_handle h, const double* x, const double* p, const double* alpha, const double* E_trial,
+                                      const double* mu_rows, const double* lambda, double* out8) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
+    if (!x || !p || !alpha || !E_trial || !mu_rows || !lambda || !out8) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    const size_t B = P.batch;
+    int rc = ensure_stage(h, B * ((size_t)2 * P.n + 3 * (size_t)P.m + 32) * sizeof(double) * 2 + 16384);
+    if (rc) return rc;
+    LsArgs A;
+    A.x = upload(h, x, B * P.n);
+    A.p = upload(h, p, B * P.n);
+    A.alpha = upload(h, alpha, B);
+    A.Etrial = upload(h, E_trial, B * P.m);
+    A.mu = upload(h, mu_rows, B * P.m);
+    A.lam = upload(h, lambda, B * P.m);
+    size_t off = h->stage_off;
+    h->stage_off = align256(off + 8 * B * sizeof(double));
+    A.out = (double*)(h->dstage + off);
+    P.active = nullptr;
+    k_linesearch<<<(int)(B < 65535 ? B : 65535), 128, 0, h->stream>>>(P, A);
+    h->launches++;
+    download(h, A.out, out8, 8 * B);
+    return finish(h);
+}
+
 extern "C" int sqpqp_kt_residuals(sqpqp_handle h, const double* lambda, const double* mult_x_U, const double* mult_x_L, double* kt) {
     if (!h) return SQPQP_E_BADARG;
     if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");

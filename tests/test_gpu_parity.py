@@ -379,6 +379,69 @@ def test_case2000_start_projection_and_first_subproblems(built_lib):
         eng.close()
 
 
+def test_linesearch_primitives_match_oracle_formulas(engine):
+    """sqpqp_linesearch_terms against the numpy restatement of compute_mu_rule2! / compute_phi / compute_derivative /
+    norm_complementarity / norm_violations (sqp_line_search.jl:280-291, sqp.jl:170-213, merit.jl:14, common.jl:30-77)."""
+    from oracle.sqp_ls import norm_complementarity, row_violations, weighted_merit
+    nlp = AcopfPolar(case9())
+    B = 2
+    rng = np.random.default_rng(3)
+    _setup(engine, nlp, batch=B)
+    x = np.asarray(nlp.x0)[None, :] + 0.05 * rng.standard_normal((B, nlp.n))
+    dE = np.zeros((B, nlp.nnz_jac_coo)); nlp.eval_jac_g(x, dE)
+    E = np.zeros((B, nlp.m)); nlp.eval_g(x, E)
+    df = np.zeros((B, nlp.n)); nlp.eval_grad_f(x, df)
+    lam = rng.standard_normal((B, nlp.m))
+    hv = np.zeros((B, nlp.nnz_hess_coo)); nlp.eval_h(x, 1.0, lam, hv)
+    engine.update_nlp(dE, hv, df, E)
+    p = 0.1 * rng.standard_normal((B, nlp.n))
+    alpha = np.array([1.0, 0.35])
+    xt = x + alpha[:, None] * p
+    Et = np.zeros((B, nlp.m)); nlp.eval_g(xt, Et)
+    mu = np.abs(rng.standard_normal((B, nlp.m))) * 10
+    t = engine.linesearch_terms(x, p, alpha, Et, mu, lam)
+    for b in range(B):
+        H = SymCooMatrix(nlp.h_row, nlp.h_col, nlp.n); H.fill(hv[b])
+        ref = {
+            "dfp": df[b] @ p[b], "pHp": p[b] @ (H.to_scipy() @ p[b]),
+            "viol1": norm_violations(E[b], nlp.g_L, nlp.g_U, x[b], nlp.x_L, nlp.x_U, 1),
+            "violinf": norm_violations(E[b], nlp.g_L, nlp.g_U, x[b], nlp.x_L, nlp.x_U, np.inf),
+            "wviol0": weighted_merit(0.0, E[b], x[b], nlp, mu[b], False),
+            "wviol_trial": weighted_merit(0.0, Et[b], xt[b], nlp, mu[b], False),
+            "viol1_trial": norm_violations(Et[b], nlp.g_L, nlp.g_U, xt[b], nlp.x_L, nlp.x_U, 1),
+            "compl": norm_complementarity(E[b], nlp.g_L, nlp.g_U, lam[b]),
+        }
+        for k, v in ref.items():
+            assert abs(t[k][b] - v) <= 1e-12 * max(1.0, abs(v)), (k, b, t[k][b], v)
+
+
+def test_line_search_driver_against_its_cpu_restatement(built_lib):
+    """BASELINE configs[1] names the SQP line-search variant.  The reference does not compile that driver (sqp.jl:226) and
+    the file is stale (oracle/sqp_ls.py header), so the parity target is the CPU restatement of the same maths:
+    known answers on the two toy problems, identical first iteration and the same neighbourhood of the optimum on case9
+    (from iteration 2 on the Hessian is evaluated with the QP's multipliers, which are not unique on case9)."""
+    from oracle.sqp_ls import LsParameters as OLs, SqpLSOracle
+    from sqpsolver_jl_b200.host.sqp_line_search import LsParameters, SqpLS
+    d = SqpLS(ReadmeToy(), LsParameters(max_iter=100)).run(); o = SqpLSOracle(ReadmeToy(), OLs(max_iter=100)).run()
+    assert d.status == o.status == 0 and d.iter == o.iter
+    assert abs(d.x[0] + 1.0) <= 1e-8 and np.abs(d.x - o.x).max() <= 1e-10
+    d.close()
+    d = SqpLS(ToyExample(), LsParameters(max_iter=200)).run(); o = SqpLSOracle(ToyExample(), OLs(max_iter=200)).run()
+    assert d.status == o.status == 0
+    assert np.allclose(d.x, [-1.0, -1.0], atol=1e-6) and np.allclose(o.x, [-1.0, -1.0], atol=1e-6)
+    d.close()
+    dl, ol = [], []
+    d = SqpLS(AcopfPolar(case9()), LsParameters(max_iter=30)).run(dl)
+    o = SqpLSOracle(AcopfPolar(case9()), OLs(max_iter=30)).run(ol)
+    assert d.status == o.status
+    for k in ("f", "phi", "alpha", "pinf", "inf_pr", "inf_du"):
+        assert abs(dl[0][k] - ol[0][k]) <= 1e-8 * max(1.0, abs(ol[0][k])), (k, dl[0][k], ol[0][k])
+    assert all(b["phi"] <= a["phi"] * (1 + 1e-12) for a, b in zip(dl[1:], dl[2:]))  # Armijo: the merit decreases
+    assert abs(d.obj_val - o.obj_val) <= 2e-3 * abs(o.obj_val)
+    assert abs(d.obj_val - 5296.686) <= 1e-2 * 5296.686  # both approach the case9 optimum
+    d.close()
+
+
 def test_solve_is_bit_reproducible(engine):
     """Deterministic reductions: two cold solves of the same QP give identical bits."""
     g = np.load(os.path.join(GOLD, "case9_mu1e4.npz"))

@@ -183,3 +183,13 @@ def test_batched_callbacks_match_single():
     # Philox streams: instance b is reproducible on its own
     pd2, _ = net.perturbed_loads(2)
     assert np.array_equal(pd2, pd[:2])
+
+
+def test_line_search_oracle_known_answers():
+    """CPU restatement of the (uncompiled, stale) line-search driver: README toy -> x = -1, toy -> (-1, -1), status 0."""
+    from oracle.sqp_ls import LsParameters, SqpLSOracle
+    from sqpsolver_jl_b200.nlp.toy import ReadmeToy, ToyExample
+    r = SqpLSOracle(ReadmeToy(), LsParameters(max_iter=100)).run()
+    assert r.status == 0 and abs(r.x[0] + 1.0) <= 1e-8 and abs(r.obj_val) <= 1e-12
+    r = SqpLSOracle(ToyExample(), LsParameters(max_iter=200)).run()
+    assert r.status == 0 and np.allclose(r.x, [-1.0, -1.0], atol=1e-6)
