@@ -260,6 +260,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=12, help="QP subproblems solved by the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spmv", action="store_true", help="skip the 2000-bus SpMV roofline leg")
+    ap.add_argument("--no-device-eval", action="store_true", help="skip the full solve with the device-side evaluator")
     ap.add_argument("--spmv-batch", type=int, default=512)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -474,6 +475,19 @@ def main():
         }
         if not args.no_spmv and world == 1:
             line["spmv"] = spmv_roofline(local, dev, peak, args.spmv_batch)
+        if not args.no_device_eval and world == 1:
+            # the same full batched SQP solve with f, grad f, g, J and H values evaluated on the device (csrc/acopf.cuh,
+            # SURVEY 8f rank 1) instead of by the host callbacks: only x and lambda go up per round
+            sqp2 = BatchSqpTR(nlp, Bl, Parameters(**kw), device=local, device_evaluator=True)
+            t0 = time.perf_counter()
+            sqp2.run()
+            line["full_sqp_solve_device_evaluator"] = {
+                "wall_s": time.perf_counter() - t0, "rounds": int(sqp2.rounds), "qp_solves": int(sqp2.n_qp.sum()),
+                "status_counts": {int(k): int(v) for k, v in zip(*np.unique(sqp2.status, return_counts=True))},
+                "device_s": sqp2.timers["device"], "callbacks_s": sqp2.timers["callbacks"],
+                "solve_kernel_s": sqp2.optimizer.stats["solve_ms"] / 1e3,
+                "max_rel_objective_diff_vs_host_evaluator": float(np.max(np.abs(sqp2.obj_val - sqp.obj_val) / np.maximum(1.0, np.abs(sqp.obj_val))))}
+            sqp2.close()
         if not args.no_cpu_baseline and world == 1:
             tcb0 = time.perf_counter()
             times = []

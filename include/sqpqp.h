@@ -184,6 +184,21 @@ int sqpqp_num_slacks(sqpqp_handle h, int32_t* S);
 int sqpqp_merit(sqpqp_handle h, const double* x, const double* p, const double* E_trial, const double* f_trial,
                 const double* mu, const int32_t* fr,
                 double* viol0, double* viol_trial, double* phi_trial, double* q0, double* qk);
+/* Device-side evaluator of the polar ACOPF NLP for the batched workload (csrc/acopf.cuh): replaces the MOI NLPEvaluator
+ * callbacks of eval_functions! (sqp.jl:86-104) and the upload of their results.  The network must be the one whose
+ * structure was given to sqpqp_setup_nlp (formulation and COO order: sqpsolver.jl_b200/nlp/acopf.py = PowerModels
+ * ACPPowerModel + build_opf of the reference's test/opf.jl:5-9).  oa/oc/os are the [nl][4] Ohm-row coefficients, the
+ * balance rows are given as CSR over their Jacobian COO entries (kind 0 constant coefficient, 1 P shunt, 2 Q shunt).
+ * sqpqp_acopf_eval_update evaluates f, grad f, g, the Jacobian and Lagrangian-Hessian (sigma = 1, mu = lambda) COO
+ * values of the instances with mask != 0 (all if null) at x, scatters them, and returns f[batch], E[batch][m],
+ * df[batch][n]; instances not in the mask keep their previous values. */
+int sqpqp_acopf_setup(sqpqp_handle h, int32_t nb, int32_t ng, int32_t nl, int32_t ref_bus, const int32_t* f_bus,
+                      const int32_t* t_bus, const int32_t* gen_bus, const double* oa, const double* oc, const double* os,
+                      const double* cost2, const double* cost1, const double* cost0, const double* gs, const double* bs,
+                      int32_t nbal, const int32_t* bal_ptr, const int32_t* bal_col, const int32_t* bal_kind,
+                      const double* bal_const, int32_t nsh, const int32_t* sh_bus);
+int sqpqp_acopf_eval_update(sqpqp_handle h, const double* x, const double* lambda, const int32_t* mask, double* f, double* E,
+                            double* df);
 /* Line-search primitives on the current device matrices (the reference's line-search driver, sqp_line_search.jl, is not
  * compiled by the reference -- sqp.jl:226 -- these are the device quantities its merit maths needs: compute_mu_rule2!
  * :280-291, compute_alpha :303-334, compute_phi sqp.jl:170-183, compute_derivative sqp.jl:190-213 + merit.jl:13-17,

@@ -82,7 +82,7 @@ EXPORTS = [
     "sqpqp_setup_nlp", "sqpqp_update_nlp", "sqpqp_update_nlp_device", "sqpqp_solve_tr", "sqpqp_num_slacks",
     "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
     "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
-    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read", "sqpqp_linesearch_terms",
+    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read", "sqpqp_linesearch_terms", "sqpqp_acopf_setup", "sqpqp_acopf_eval_update",
 ]
 
 
@@ -139,6 +139,9 @@ def lib():
     L.sqpqp_chol_stats.argtypes = [vp, _lp, _lp, _lp]
     L.sqpqp_chol_layout.argtypes = [vp, _lp, _lp]
     L.sqpqp_prof_read.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.sqpqp_acopf_setup.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp,
+                                    C.c_int32, _ip, _ip, _ip, _dp, C.c_int32, _ip]
+    L.sqpqp_acopf_eval_update.argtypes = [vp, _dp, _dp, _ip, _dp, _dp, _dp]
     L.sqpqp_linesearch_terms.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
     L.sqpqp_debug_read.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_int64]
     L.sqpqp_spmv.argtypes = [vp, C.c_int32, _dp, _dp]
@@ -339,6 +342,42 @@ class Engine:
         kt = np.zeros(B)
         self._ck(self.L.sqpqp_kt_residuals(self.h, _d(lam), _d(mxU), _d(mxL), _d(kt)))
         return kt
+
+    def acopf_setup(self, nlp):
+        """Hand the network of an :class:`AcopfPolar` NLP (the one given to setup_nlp) to the device-side evaluator."""
+        net = nlp.net
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        nb, ng, nl = nlp.nb, nlp.ng, nlp.nl
+        # balance rows as CSR over their Jacobian COO entries (acopf.py: _build_jacobian_structure)
+        ptr, col, kind = [0], [], []
+        for i in range(nb):
+            for part, (ov, og) in enumerate(((nlp.o_p, nlp.o_pg), (nlp.o_q, nlp.o_qg))):
+                for a in nlp.arcs_at[i]:
+                    col.append(ov + a); kind.append(0)
+                for k in nlp.gens_at[i]:
+                    col.append(og + k); kind.append(0)
+                if nlp.has_shunt[i]:
+                    col.append(nlp.o_vm + i); kind.append(1 if part == 0 else 2)
+                ptr.append(len(col))
+        keep = (f64(net.f_bus), )  # noqa: F841  (arrays below are copied by the library during the call)
+        args = [i32(net.f_bus), i32(net.t_bus), i32(net.gen_bus), f64(nlp.oa), f64(nlp.oc), f64(nlp.os), f64(net.cost2),
+                f64(net.cost1), f64(net.cost0), f64(net.gs), f64(net.bs)]
+        bal = [i32(ptr), i32(col), i32(kind), f64(nlp.j_bal_const), i32(nlp.sh_bus)]
+        assert len(col) == nlp.j_bal_const.shape[0]
+        self._ck(self.L.sqpqp_acopf_setup(self.h, nb, ng, nl, int(net.ref_bus), _i(args[0]), _i(args[1]), _i(args[2]), _d(args[3]),
+                                          _d(args[4]), _d(args[5]), _d(args[6]), _d(args[7]), _d(args[8]), _d(args[9]), _d(args[10]),
+                                          len(col), _i(bal[0]), _i(bal[1]), _i(bal[2]), _d(bal[3]), int(nlp.sh_bus.shape[0]),
+                                          _i(bal[4])))
+
+    def acopf_eval_update(self, x, lam, mask=None):
+        """eval_functions! on the device for the masked instances + scatter; returns (f[B], E[B,m], df[B,n])."""
+        B, n, m = self.batch, self.n, self.m
+        x = _f64(x).reshape(B, n); lam = _f64(lam).reshape(B, m)
+        mk = np.ascontiguousarray(mask, dtype=np.int32) if mask is not None else None
+        f = np.zeros(B); E = np.zeros((B, m)); df = np.zeros((B, n))
+        self._ck(self.L.sqpqp_acopf_eval_update(self.h, _d(x), _d(lam), _i(mk) if mk is not None else None, _d(f), _d(E), _d(df)))
+        return f, E, df
 
     def linesearch_terms(self, x, p, alpha, E_trial, mu_rows, lam):
         """Device line-search primitives (include/sqpqp.h: sqpqp_linesearch_terms); returns a dict of [batch] arrays."""

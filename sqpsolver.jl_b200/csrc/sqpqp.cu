@@ -18,6 +18,7 @@
 #include "ipm.cuh"
 #include "merit.cuh"
 #include "spmv.cuh"
+#include "acopf.cuh"
 #include "symbolic.hpp"
 
 struct Pending {
@@ -56,7 +57,9 @@ struct sqpqp_handle_s {
     int cta2_smem = 100 * 1024; // ... when two share an SM (the default for large batches)
     int64_t chol_flops = 0;
     std::vector<double> avg_row;  // avg row length of J(normal), J(ext), T, H
-    SpmvPlan planJ{}, planT{}, planH{};  // CSR-stream row blocks of J (normal phase), J' and H
+    SpmvPlan planJ{}, planT{}, planH{};
+    AcopfDev acopf{};       // device-side ACOPF evaluator (acopf.cuh); nb == 0: not set up
+    double* d_f = nullptr;  // [batch] objective values of the evaluator  // CSR-stream row blocks of J (normal phase), J' and H
     // generic-lane bookkeeping
     bool generic = false;
 };
@@ -665,6 +668,82 @@ extern "C" int sqpqp_update_nlp_device(sqpqp_handle h, const double* dE, const d
     CUDA_OK(cudaGetLastError());
     h->updated = true;
     return 0;
+}
+
+// ---- device-side ACOPF evaluator (acopf.cuh) ---------------------------------------------------
+extern "C" int sqpqp_acopf_setup(sqpqp_handle h, int32_t nb, int32_t ng, int32_t nl, int32_t ref_bus, const int32_t* f_bus,
+                                 const int32_t* t_bus, const int32_t* gen_bus, const double* oa, const double* oc, const double* os,
+                                 const double* cost2, const double* cost1, const double* cost0, const double* gs, const double* bs,
+                                 int32_t nbal, const int32_t* bal_ptr, const int32_t* bal_col, const int32_t* bal_kind,
+                                 const double* bal_const, int32_t nsh, const int32_t* sh_bus) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    Prob& P = h->P;
+    if (nb < 1 || ng < 0 || nl < 0 || ref_bus < 0 || ref_bus >= nb) return fail(h, SQPQP_E_BADARG, "bad network size");
+    // the evaluator writes the COO values in the order fixed by the layout documented in acopf.cuh: check the sizes
+    if (P.n != 2 * nb + 2 * ng + 4 * nl || P.m != 1 + 2 * nb + 8 * nl || h->nnzJ_coo != (int64_t)8 * nl + 1 + nbal + 20 * nl ||
+        h->nnzH_coo != (int64_t)ng + 4 * nl + 2 * nsh + 36 * nl)
+        return fail(h, SQPQP_E_BADARG, "network does not match the NLP given to sqpqp_setup_nlp (n, m, COO lengths)");
+    DeviceGuard g(h->device);
+    AcopfDev& A = h->acopf;
+    auto upi = [&](const int32_t* src, size_t cnt, const int** dst) -> int {
+        int* d = nullptr;
+        int rc = dalloc(h, &d, cnt);
+        if (rc) return rc;
+        if (cnt) CUDA_OK(cudaMemcpyAsync(d, src, cnt * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        *dst = d;
+        return 0;
+    };
+    auto upd = [&](const double* src, size_t cnt, const double** dst) -> int {
+        double* d = nullptr;
+        int rc = dalloc(h, &d, cnt);
+        if (rc) return rc;
+        if (cnt) CUDA_OK(cudaMemcpyAsync(d, src, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CUDA_OK(cudaStreamSynchronize(h->stream));
+        *dst = d;
+        return 0;
+    };
+    int rc;
+    if ((rc = upi(f_bus, nl, &A.f_bus)) || (rc = upi(t_bus, nl, &A.t_bus)) || (rc = upi(gen_bus, ng, &A.gen_bus)) ||
+        (rc = upd(oa, (size_t)4 * nl, &A.oa)) || (rc = upd(oc, (size_t)4 * nl, &A.oc)) || (rc = upd(os, (size_t)4 * nl, &A.os)) ||
+        (rc = upd(cost2, ng, &A.cost2)) || (rc = upd(cost1, ng, &A.cost1)) || (rc = upd(cost0, ng, &A.cost0)) ||
+        (rc = upd(gs, nb, &A.gs)) || (rc = upd(bs, nb, &A.bs)) || (rc = upi(bal_ptr, (size_t)2 * nb + 1, &A.bal_ptr)) ||
+        (rc = upi(bal_col, nbal, &A.bal_col)) || (rc = upi(bal_kind, nbal, &A.bal_kind)) || (rc = upd(bal_const, nbal, &A.bal_const)) ||
+        (rc = upi(sh_bus, nsh, &A.sh_bus)))
+        return rc;
+    DALLOC(h->d_f, P.batch);
+    A.nb = nb; A.ng = ng; A.nl = nl; A.ref_bus = ref_bus; A.nbal = nbal; A.nsh = nsh;
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// eval_functions! (sqp.jl:86-104) on the device for the masked instances + the value scatter; f, E and grad f come back
+extern "C" int sqpqp_acopf_eval_update(sqpqp_handle h, const double* x, const double* lambda, const int32_t* mask, double* f,
+                                       double* E, double* df) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || h->acopf.nb == 0) return fail(h, SQPQP_E_STATE, "setup / acopf_setup not called");
+    if (!x || !lambda) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    const size_t B = P.batch;
+    int rc = ensure_stage(h, B * ((size_t)3 * P.n + 3 * (size_t)P.m + 32) * sizeof(double) + B * 16 + 16384);
+    if (rc) return rc;
+    AcopfArgs G;
+    G.x = upload(h, x, B * P.n);
+    G.lam = upload(h, lambda, B * P.m);
+    G.mask = mask ? upload(h, mask, B) : nullptr;
+    G.dE = h->d_dE; G.hval = h->d_hval; G.df = h->d_df; G.E = h->d_E; G.f = h->d_f;
+    G.nnzJ = (int)h->nnzJ_coo; G.nnzH = (int)h->nnzH_coo;
+    k_acopf_eval<<<(int)(B < 65535 ? B : 65535), 256, 0, h->stream>>>(h->acopf, G, P.n, P.m, (int)B);
+    h->launches++;
+    P.df = h->d_df; P.E = h->d_E;
+    launch_scatter(h, h->d_dE, h->d_hval);
+    download(h, h->d_f, f, B);
+    download(h, h->d_E, E, B * P.m);
+    download(h, h->d_df, df, B * P.n);
+    h->updated = true;
+    return finish(h);
 }
 
 // ---- solve -------------------------------------------------------------------------------

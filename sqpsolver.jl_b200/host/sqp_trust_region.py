@@ -41,7 +41,7 @@ def _ninf(v):
 
 class BatchSqpTR:
     def __init__(self, nlp, batch: int, params: Parameters | None = None, device: int = 0,
-                 engine_options: dict | None = None, x0=None):
+                 engine_options: dict | None = None, x0=None, device_evaluator: bool = False):
         self.problem = nlp
         self.options = params or Parameters()
         self.B = B = batch
@@ -76,6 +76,11 @@ class BatchSqpTR:
         self.n_qp = np.zeros(B, np.int64)
         self.optimizer = QpDevice(nlp, batch=B, device=device, engine_options=engine_options)
         self.optimizer.create_model(None)
+        # f, grad f, g and the J / H COO values evaluated on the device (csrc/acopf.cuh) instead of by the
+        # host callbacks -- only x and lambda go up, only f, E, grad f come back
+        self.device_evaluator = bool(device_evaluator)
+        if self.device_evaluator:
+            self.optimizer.engine.acopf_setup(nlp)
         self.rounds = 0
         self.timers = {"callbacks": 0.0, "device": 0.0}
         self.trace = None
@@ -90,6 +95,12 @@ class BatchSqpTR:
         pr = self.problem
         t0 = time.perf_counter()
         idx = np.nonzero(mask)[0]
+        if self.device_evaluator:
+            if idx.size:
+                f, E, df = self.optimizer.engine.acopf_eval_update(self.x, self.lam, np.asarray(mask, np.int32))
+                self.f[idx], self.E[idx], self.df[idx] = f[idx], E[idx], df[idx]
+            self.timers["device"] += time.perf_counter() - t0
+            return
         if idx.size:
             xs = self.x[idx]
             f = np.atleast_1d(pr.eval_f(xs))
