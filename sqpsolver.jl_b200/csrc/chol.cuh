@@ -70,18 +70,55 @@ __device__ __forceinline__ double column_dot(const double* __restrict__ V, const
     return acc0 + acc1;
 }
 
+// Two pair lists walked together, two pairs of each per trip: eight independent gathers in flight.  A thread that owns
+// two slots of a phase pays the index -> value round trips once for both.
+__device__ __forceinline__ void gather_dot2(const int2* __restrict__ ab, int qa, const int ea, const int sa, int qb, const int eb,
+                                            const int sb, const double* A, const double* B, double& ra, double& rb) {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    while (qa < ea || qb < eb) {
+        const bool a_1 = qa < ea, a_2 = qa + sa < ea, b_1 = qb < eb, b_2 = qb + sb < eb;
+        const int2 pa1 = ab[a_1 ? qa : 0], pa2 = ab[a_2 ? qa + sa : 0], pb1 = ab[b_1 ? qb : 0], pb2 = ab[b_2 ? qb + sb : 0];
+        const double xa1 = A[pa1.x], ya1 = B[pa1.y], xa2 = A[pa2.x], ya2 = B[pa2.y];
+        const double xb1 = A[pb1.x], yb1 = B[pb1.y], xb2 = A[pb2.x], yb2 = B[pb2.y];
+        if (a_1) a0 = fma(xa1, ya1, a0);
+        if (a_2) a1 = fma(xa2, ya2, a1);
+        if (b_1) b0 = fma(xb1, yb1, b0);
+        if (b_2) b1 = fma(xb2, yb2, b1);
+        qa += 2 * sa;
+        qb += 2 * sb;
+    }
+    ra = a0 + a1;
+    rb = b0 + b1;
+}
+
 // L <- lower triangle of K in the permuted order, sourced entries only (pure fill entries have
 // K_e = 0 and are never read: their factor task carries has_K = 0).  Pv may be null (no P); dg[j] + shift
 // is added to the diagonal entry of ORIGINAL column j.  Also clears the dense tail.
 template <class Team>
 __device__ void chol_assemble(Team& T, const CholDev& C, const CholWork& W, const double* __restrict__ Pv,
                               const double* __restrict__ dg, const double shift, const double* __restrict__ w,
-                              const double* __restrict__ Jv) {
-    double* __restrict__ L = W.L;
-    double* __restrict__ wJ = W.wJ;
-    for (int a = T.tid(); a < C.nslotJ; a += T.size()) {
-        const int r = C.jrow[a];
-        wJ[a] = r >= 0 ? w[r] * Jv[a] : 0.0;
+                              const double* __restrict__ Jv, Prof& pf) {
+    double* L = W.L;
+    double* wJ = W.wJ;
+    // four slots per trip, all loads before the first store: the arrays may alias as far as the compiler knows, so a
+    // plain loop would serialise the index -> weight round trips of consecutive iterations
+    for (int a0 = T.tid(); a0 < C.nslotJ; a0 += 4 * T.size()) {
+        int r[4];
+        double jv[4], wr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * T.size();
+            const bool ok = a < C.nslotJ;
+            r[u] = ok ? C.jrow[a] : -1;
+            jv[u] = ok ? Jv[a] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wr[u] = r[u] >= 0 ? w[r[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * T.size();
+            if (a < C.nslotJ) wJ[a] = wr[u] * jv[u];
+        }
     }
     if (C.T > 0) {  // packed tail, padded to a multiple of 4 columns with identity rows (dense_factor works in panels of 4)
         const int Tp = (C.T + 3) & ~3;
@@ -90,33 +127,39 @@ __device__ void chol_assemble(Team& T, const CholDev& C, const CholWork& W, cons
         for (int i = C.T + T.tid(); i < Tp; i += T.size()) W.D[i * (i + 1) / 2 + i] = 1.0;
     }
     T.sync();
-    // two tasks per thread and round, their (short) term lists walked together so that both gather
-    // chains are in flight
-    const int nt = C.n + C.n_aoff, stride = T.size();
-    const int2* __restrict__ ab = C.as_ab;
-    for (int t = T.tid(); t < nt; t += 2 * stride) {
-        const int t2 = t + stride;
-        const bool has2 = t2 < nt;
-        const int4 k1 = t < C.n ? C.atask_diag[t] : C.atask_off[t - C.n];
-        const int4 k2 = has2 ? (t2 < C.n ? C.atask_diag[t2] : C.atask_off[t2 - C.n]) : make_int4(0, 0, 0, -1);
-        double v1 = (Pv && k1.w >= 0) ? Pv[k1.w] : 0.0;
-        double v2 = (Pv && k2.w >= 0) ? Pv[k2.w] : 0.0;
-        if (t < C.n) v1 += dg[C.perm[t]] + shift;
-        if (has2 && t2 < C.n) v2 += dg[C.perm[t2]] + shift;
-        int q1 = k1.y, q2 = k2.y;
-        const int e1 = k1.z, e2 = k2.z;
-        while (q1 < e1 || q2 < e2) {
-            const bool o1 = q1 < e1, o2 = q2 < e2;
-            const int2 p1 = ab[o1 ? q1 : 0], p2 = ab[o2 ? q2 : 0];
-            const double a1 = wJ[p1.x], b1 = Jv[p1.y], a2 = wJ[p2.x], b2 = Jv[p2.y];
-            if (o1) v1 = fma(a1, b1, v1);
-            if (o2) v2 = fma(a2, b2, v2);
-            ++q1; ++q2;
+    pf.lap(PS_ASSEMBLE);
+    // one slot per thread and round: a lane's share of the terms of one sourced entry (symbolic.hpp 4b), lane groups of
+    // mixed power-of-two sizes reduced by one shared butterfly, the leader adds P, the diagonal term and the shift
+    for (int r0 = 0; r0 < C.n_aslot; r0 += 2 * T.size()) {  // two slots per thread and trip (gather_dot2)
+        const int sA = r0 + T.tid(), sB = sA + T.size();
+        const bool onA = sA < C.n_aslot, onB = sB < C.n_aslot;
+        const int4 slA = C.aslot[onA ? sA : 0], slB = C.aslot[onB ? sB : 0];
+        const int LnA = 1 << ((slA.x >> 26) & 7), LnB = 1 << ((slB.x >> 26) & 7);
+        const bool ldA = onA && ((slA.x >> 29) & 1), ldB = onB && ((slB.x >> 29) & 1);
+        double vA = 0.0, vB = 0.0;
+        if (ldA) {
+            const int d = C.aslot_d[sA];
+            if (Pv && slA.w >= 0) vA = Pv[slA.w];
+            if (d >= 0) vA += dg[d] + shift;
         }
-        L[k1.x] = v1;
-        if (has2) L[k2.x] = v2;
+        if (ldB) {
+            const int d = C.aslot_d[sB];
+            if (Pv && slB.w >= 0) vB = Pv[slB.w];
+            if (d >= 0) vB += dg[d] + shift;
+        }
+        double accA, accB;
+        gather_dot2(C.as_ab, onA ? slA.y : 0, onA ? slA.z : 0, LnA, onB ? slB.y : 0, onB ? slB.z : 0, LnB, wJ, Jv, accA, accB);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double tA = __shfl_xor_sync(0xffffffffu, accA, o), tB = __shfl_xor_sync(0xffffffffu, accB, o);
+            if (o < LnA) accA += tA;
+            if (o < LnB) accB += tB;
+        }
+        if (ldA) L[slA.x & 0x3ffffff] = vA + accA;
+        if (ldB) L[slB.x & 0x3ffffff] = vB + accB;
     }
     T.sync();
+    pf.lap(PS_ASSEMBLE_SLOTS);
 }
 
 // ---- dense tail, CTA teams only -------------------------------------------------------------
@@ -258,31 +301,47 @@ __device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& 
     for (int p = 0; p < C.nphase; ++p) {
         const int4 nxt = C.fphase[p + 1];  // (padded by one entry) off the critical path of the next phase
         const int s0 = ph.x, ns = ph.y - ph.x, kind = ph.w;
-        for (int r0 = 0; r0 < ns; r0 += T.size()) {
-            const int sidx = r0 + T.tid();
-            const bool on = sidx < ns;
-            const int4 sl = C.ftask[s0 + (on ? sidx : 0)];
-            const int e = sl.x & 0x3ffffff, Ln = 1 << ((sl.x >> 26) & 7);
-            const bool leader = on && ((sl.x >> 29) & 1);
-            const double k0 = (leader && (sl.x >> 30)) ? L[e] : 0.0;
-            const double di = (leader && kind == 1) ? W.dinv[sl.w] : 0.0;
-            double acc = on ? gather_dot(C.fp_ab, sl.y, sl.z, Ln, L, L) : 0.0;
+        for (int r0 = 0; r0 < ns; r0 += 2 * T.size()) {  // two slots per thread and trip (gather_dot2)
+            const int sA = r0 + T.tid(), sB = sA + T.size();
+            const bool onA = sA < ns, onB = sB < ns;
+            const int4 slA = C.ftask[s0 + (onA ? sA : 0)], slB = C.ftask[s0 + (onB ? sB : 0)];
+            const int eA = slA.x & 0x3ffffff, eB = slB.x & 0x3ffffff;
+            const int LnA = 1 << ((slA.x >> 26) & 7), LnB = 1 << ((slB.x >> 26) & 7);
+            const bool ldA = onA && ((slA.x >> 29) & 1), ldB = onB && ((slB.x >> 29) & 1);
+            const double kA = (ldA && (slA.x >> 30)) ? L[eA] : 0.0, kB = (ldB && (slB.x >> 30)) ? L[eB] : 0.0;
+            const double dA = (ldA && kind == 1) ? W.dinv[slA.w] : 0.0, dB = (ldB && kind == 1) ? W.dinv[slB.w] : 0.0;
+            double accA, accB;
+            gather_dot2(C.fp_ab, onA ? slA.y : 0, onA ? slA.z : 0, LnA, onB ? slB.y : 0, onB ? slB.z : 0, LnB, L, L, accA, accB);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {  // lane groups of mixed (power of two, aligned) sizes share the butterfly
-                const double t = __shfl_xor_sync(0xffffffffu, acc, o);
-                if (o < Ln) acc += t;
+                const double tA = __shfl_xor_sync(0xffffffffu, accA, o), tB = __shfl_xor_sync(0xffffffffu, accB, o);
+                if (o < LnA) accA += tA;
+                if (o < LnB) accB += tB;
             }
-            if (leader) {
-                double v = k0 - acc;
+            if (ldA) {
+                double v = kA - accA;
                 if (kind == 0) {
                     if (!(v > 0.0)) { bad[0] = 1.0; v = 1.0; }
                     const double inv = rsqrt(v);
-                    L[e] = v * inv;
-                    W.dinv[sl.w] = inv;
+                    L[eA] = v * inv;
+                    W.dinv[slA.w] = inv;
                 } else if (kind == 1) {
-                    L[e] = v * di;
+                    L[eA] = v * dA;
                 } else {
-                    W.D[sl.w] = v;
+                    W.D[slA.w] = v;
+                }
+            }
+            if (ldB) {
+                double v = kB - accB;
+                if (kind == 0) {
+                    if (!(v > 0.0)) { bad[0] = 1.0; v = 1.0; }
+                    const double inv = rsqrt(v);
+                    L[eB] = v * inv;
+                    W.dinv[slB.w] = inv;
+                } else if (kind == 1) {
+                    L[eB] = v * dB;
+                } else {
+                    W.D[slB.w] = v;
                 }
             }
         }

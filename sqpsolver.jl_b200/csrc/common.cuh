@@ -41,7 +41,7 @@ struct Csr {
 // dense tail n0 .. n-1 (T columns, factorised as a packed dense matrix in shared memory).
 struct CholDev {
     int n, nnzL, nlev, n0, T;
-    int nphase, n_aoff, nslotJ;
+    int nphase, n_aslot, nslotJ;
     const int *perm;
     const int *Lp, *Li;
     const int *Rp, *Rmid;
@@ -50,8 +50,8 @@ struct CholDev {
     const int2 *fp_ab;      // pairs of value indices
     const int4 *ftask;      // factorisation tasks  (entry | has_K << 30, first pair, end pair, aux)
     const int4 *fphase;     // factorisation phases (first task, end task, max pairs, kind)
-    const int4 *atask_off;  // assembly of sourced sub-diagonal entries (entry, first term, end term, P index | -1)
-    const int4 *atask_diag; // assembly of the diagonal, one per column
+    const int4 *aslot;      // assembly slots (entry | lg << 26 | leader << 29, first term of the lane, end term, P index | -1)
+    const int *aslot_d;     // per assembly slot: original column for the diagonal term d[], or -1
     const int2 *as_ab;      // assembly terms (wJ index, Jv index)
     const int *jrow;        // row of every J value slot
 };
@@ -124,7 +124,7 @@ struct Placement {
 // Thread 0 of every CTA adds the clock64 cycles it spent in each segment of the solve to a global
 // table; the sum over CTAs gives the share of CTA-time per segment.  Compiled out by default.
 enum ProfSeg {
-    PS_PROLOGUE = 0, PS_RESID, PS_WEIGHTS, PS_ASSEMBLE, PS_FACTOR_SPARSE, PS_SCHUR, PS_FACTOR_DENSE, PS_RHS, PS_FWD, PS_TAIL,
+    PS_PROLOGUE = 0, PS_RESID, PS_WEIGHTS, PS_ASSEMBLE, PS_FACTOR_SPARSE, PS_ASSEMBLE_SLOTS, PS_FACTOR_DENSE, PS_RHS, PS_FWD, PS_TAIL,
     PS_BWD, PS_RATIO, PS_UPDATE, PS_EPILOGUE, PS_OTHER, PS_COUNT
 };
 #ifdef SQPQP_PROF

@@ -256,8 +256,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         // ---- assembly, factorisation (with inertia correction: the shift rho_p is a scalar on the diagonal) ----
         bool fact_ok = false;
         for (int tries = 0; tries < 30 && !fact_ok; ++tries) {
-            chol_assemble(T, C, W, I.useH ? I.Hsv : (const double*)nullptr, I.nv[N_DSH], rho_p, I.mv[M_RW], I.Jsv);
-            pf.lap(PS_ASSEMBLE);
+            chol_assemble(T, C, W, I.useH ? I.Hsv : (const double*)nullptr, I.nv[N_DSH], rho_p, I.mv[M_RW], I.Jsv, pf);
             fact_ok = chol_factor(T, C, W, pf);
             ++out.nfact;
             if (!fact_ok) rho_p = fmax(fmax(10.0 * rho_p, rho_last > 0.0 ? rho_last / 3.0 : 1e-4), 1e-6);

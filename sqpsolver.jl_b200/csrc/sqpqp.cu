@@ -524,15 +524,17 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         };
         auto upload_symbolic = [&](Symbolic& Sy, CholDev& C, int ncols) -> int {
             C.n = ncols; C.nnzL = Sy.nnzL; C.nlev = Sy.nlev; C.n0 = Sy.n0; C.T = Sy.T;
-            C.nphase = (int)Sy.fphase.size() / 4; C.n_aoff = (int)Sy.atask_off.size() / 4; C.nslotJ = (int)Sy.jrow.size();
+            C.nphase = (int)Sy.fphase.size() / 4; C.n_aslot = (int)Sy.aslot_d.size(); C.nslotJ = (int)Sy.jrow.size();
             for (int k = 0; k < 4; ++k) Sy.fphase.push_back(0);  // the phase loop reads one entry ahead
             if (Sy.as_ab.empty()) { Sy.as_ab.push_back(0); Sy.as_ab.push_back(0); }
+            if (Sy.fp_ab.empty()) { Sy.fp_ab.push_back(0); Sy.fp_ab.push_back(0); }  // gather_dot2 reads pair 0 for idle lanes
             if (Sy.ftask.empty()) Sy.ftask.assign(4, 0);
+            if (Sy.aslot.empty()) { Sy.aslot.assign(4, 0); Sy.aslot_d.assign(1, -1); }
             const std::vector<int>* srcs[] = {&Sy.perm, &Sy.Lp, &Sy.Li, &Sy.Rp, &Sy.Rmid, &Sy.Rci, &Sy.lev_ptr, &Sy.fp_ab,
-                                              &Sy.ftask, &Sy.fphase, &Sy.atask_off, &Sy.atask_diag, &Sy.as_ab, &Sy.jrow};
+                                              &Sy.ftask, &Sy.fphase, &Sy.aslot, &Sy.aslot_d, &Sy.as_ab, &Sy.jrow};
             const int** dsts[] = {&C.perm, &C.Lp, &C.Li, &C.Rp, &C.Rmid, (const int**)&C.Rci, &C.lev_ptr, (const int**)&C.fp_ab,
-                                  (const int**)&C.ftask, (const int**)&C.fphase, (const int**)&C.atask_off,
-                                  (const int**)&C.atask_diag, (const int**)&C.as_ab, &C.jrow};
+                                  (const int**)&C.ftask, (const int**)&C.fphase, (const int**)&C.aslot,
+                                  &C.aslot_d, (const int**)&C.as_ab, &C.jrow};
             for (int k = 0; k < 14; ++k) {
                 int rc2 = up(*srcs[k], dsts[k]);  // cudaMalloc alignment (256 B) covers the int2 / int4 views
                 if (rc2) return rc2;

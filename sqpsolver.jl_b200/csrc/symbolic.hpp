@@ -47,8 +47,11 @@ struct Symbolic {
     std::vector<int> ftask, fphase;
     int ftasks = 0;                      // number of tasks (entries) behind the slots
     // assembly: K_e = P[h] + sum_t wJ[a_t] * Jv[b_t]  (+ d[perm[j]] on the diagonal), wJ = w[row] .* Jv
-    std::vector<int> atask_off;          // sourced sub-diagonal entries: (entry id, first term, end term, P value index | -1)
-    std::vector<int> atask_diag;         // per column j: (entry id, first term, end term, P value index | -1)
+    // assembly slots, same lane-group scheme as the factor slots (a diagonal entry of a bus variable has 40+ terms, most
+    // sourced entries have one or two):  slot = (entry id | lg << 26 | leader << 29, first term of this lane, end term,
+    // P value index | -1);  aslot_d[slot] = original column whose d[] goes to this (diagonal) entry, or -1
+    std::vector<int> aslot, aslot_d;
+    int atasks = 0;
     std::vector<int> as_ab;              // interleaved (Jv index a, Jv index b) per term
     std::vector<int> jrow;               // row of every J value slot (for wJ); slots beyond a row's end: -1
     int as_terms = 0;
@@ -250,16 +253,28 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
         }
     }
     std::vector<char> hasK(S.nnzL, 0);
-    S.atask_diag.clear();
-    S.atask_off.clear();
-    for (int j = 0; j < n; ++j)
-        for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
-            const bool diag = e == S.Lp[j];
-            if (!diag && as_h[e] < 0 && as_ptr[e] == as_ptr[e + 1]) continue;  // pure fill: K_e = 0, nothing to assemble
-            hasK[e] = 1;
-            std::vector<int>& dst = diag ? S.atask_diag : S.atask_off;
-            dst.push_back(e); dst.push_back(as_ptr[e]); dst.push_back(as_ptr[e + 1]); dst.push_back(as_h[e]);
+    {
+        struct At { int e, q0, q1, h, d; };
+        std::vector<At> v;
+        for (int j = 0; j < n; ++j)
+            for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
+                const bool diag = e == S.Lp[j];
+                if (!diag && as_h[e] < 0 && as_ptr[e] == as_ptr[e + 1]) continue;  // pure fill: K_e = 0, nothing to assemble
+                hasK[e] = 1;
+                v.push_back(At{e, as_ptr[e], as_ptr[e + 1], as_h[e], diag ? S.perm[j] : -1});
+            }
+        std::stable_sort(v.begin(), v.end(), [](const At& a, const At& b) { return a.q1 - a.q0 > b.q1 - b.q0; });
+        S.atasks = (int)v.size();
+        for (const At& t : v) {
+            int lg = 0;
+            while (lg < 5 && (t.q1 - t.q0) > (4 << lg)) ++lg;
+            for (int lane = 0; lane < (1 << lg); ++lane) {
+                S.aslot.push_back(t.e | (lg << 26) | (lane == 0 ? (1 << 29) : 0));
+                S.aslot.push_back(t.q0 + lane); S.aslot.push_back(t.q1); S.aslot.push_back(t.h);
+                S.aslot_d.push_back(t.d);
+            }
         }
+    }
     {
         int nslots = 0;
         for (int r = 0; r < m; ++r) nslots = std::max(nslots, Jre[r]);

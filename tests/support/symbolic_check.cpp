@@ -22,15 +22,20 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
     // assembly (chol_assemble): wJ, then the diagonal and the sourced sub-diagonal entries; pure fill stays unset (NaN here:
     // a factor task that read it although has_K = 0 would poison the result)
     for (size_t a = 0; a < S.jrow.size(); ++a) wJ[a] = S.jrow[a] >= 0 ? w[S.jrow[a]] * Jv[a] : 0.0;
-    auto assemble = [&](const int* tk, bool diag, int col) {
+    for (size_t t = 0; t < S.aslot_d.size();) {  // assembly slots: a task = 2^lg consecutive slots, leader first
+        const int* tk = &S.aslot[4 * t];
+        const int e = tk[0] & 0x3ffffff, Ln = 1 << ((tk[0] >> 26) & 7);
+        if (!((tk[0] >> 29) & 1) || t % Ln != 0) return -4;
         double v = (Pv && tk[3] >= 0) ? Pv[tk[3]] : 0.0;
-        if (diag) v += d[S.perm[col]];
-        for (int t = tk[1]; t < tk[2]; ++t) v += wJ[S.as_ab[2 * (size_t)t]] * Jv[S.as_ab[2 * (size_t)t + 1]];
-        L[tk[0]] = v;
-    };
-    if ((int)S.atask_diag.size() != 4 * n) return -4;
-    for (int j = 0; j < n; ++j) assemble(&S.atask_diag[4 * (size_t)j], true, j);
-    for (size_t t = 0; t < S.atask_off.size() / 4; ++t) assemble(&S.atask_off[4 * t], false, 0);
+        if (S.aslot_d[t] >= 0) v += d[S.aslot_d[t]];
+        for (int lane = 0; lane < Ln; ++lane) {
+            const int* sl = &S.aslot[4 * (t + lane)];
+            if ((sl[0] & 0x3ffffff) != e || sl[1] != tk[1] + lane) return -4;
+            for (int q = sl[1]; q < sl[2]; q += Ln) v += wJ[S.as_ab[2 * (size_t)q]] * Jv[S.as_ab[2 * (size_t)q + 1]];
+        }
+        L[e] = v;
+        t += Ln;
+    }
     // factorisation phases (chol_factor).  done[e] = phase that produced entry e: a task may only read entries of
     // EARLIER phases (the device runs the tasks of one phase concurrently).
     std::vector<int> done(S.nnzL, 1 << 30), ddone(n, 1 << 30);

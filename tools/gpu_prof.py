@@ -9,7 +9,7 @@ from sqpsolver_jl_b200 import capi
 from sqpsolver_jl_b200.nlp.networks import synth_net
 from sqpsolver_jl_b200.nlp.acopf import AcopfPolar
 from sqpsolver_jl_b200.host.sqp_trust_region import BatchSqpTR, Parameters
-SEG = ["prologue", "resid", "weights", "assemble", "factor_sparse", "schur", "factor_dense", "rhs", "fwd", "tail", "bwd",
+SEG = ["prologue", "resid", "weights", "assemble", "factor_sparse", "assemble_slots", "factor_dense", "rhs", "fwd", "tail", "bwd",
        "ratio", "update", "epilogue", "other"]
 B = int(sys.argv[1]); iters = int(sys.argv[2])
 eo = {}
