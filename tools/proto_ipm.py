@@ -36,6 +36,7 @@ class Opts:
     rho_bump = 10.0    # growth on a failed factorisation
     rho_hold = 0       # iterations the shift is held after a failed factorisation
     rho_floor_frac = 0.0  # never decay below this fraction of the last shift that was NEEDED
+    mu_force = 0       # force a barrier decrease after this many iterations without one (0 = never)
 
 
 class _SymLU:
@@ -183,6 +184,7 @@ def ipm_solve(P, q, J, rl, ru, xl, xu, o: Opts = Opts()):
         S = (s_ru, s_rl, s_xu, s_xl); Z = (z_ru, z_rl, z_xu, z_xl); MK = (ru_f, rl_f, xu_f, xl_f)
         if o.monotone:
             # barrier subproblem error; decrease mu_t when it is solved well enough
+            mu_before = mu_t
             while True:
                 comp = max(_ninf((s * z - mu_t) * mk) for s, z, mk in zip(S, Z, MK))
                 e_mu = max(rd * c if False else _ninf(r_x), _ninf(r_eq), _ninf(r_ru), _ninf(r_rl), _ninf(r_eqx), _ninf(r_xu), _ninf(r_xl), comp)
@@ -190,6 +192,13 @@ def ipm_solve(P, q, J, rl, ru, xl, xu, o: Opts = Opts()):
                     mu_t = max(1e-13, min(0.2 * mu_t, mu_t ** 1.5))
                 else:
                     break
+            if mu_t < mu_before:
+                stall = 0
+            else:
+                stall = locals().get('stall', 0) + 1
+                if o.mu_force and stall >= o.mu_force and mu_t > 1e-13:
+                    mu_t = max(1e-13, 0.2 * mu_t)
+                    stall = 0
             rc = [mu_t - s * z for s, z in zip(S, Z)]
             dx, dZ, dS, dy, dyx = solve_dir(*rc)
             tau = max(o.tau, 1.0 - mu_t)
