@@ -92,10 +92,13 @@ typedef struct sqpqp_options {
     int32_t ipm_max_iter;
     int32_t fallback_max_iter; /* ADMM iteration cap when it runs as the fallback of a failed interior-point solve */
     double ipm_eps, ipm_delta0, ipm_delta_min, ipm_rho0, ipm_tau, ipm_mu0, ipm_mu_min, ipm_kappa_eps;
-    int32_t ipm_refine;      /* iterative-refinement steps per Newton solve */
+    int32_t ipm_refine;      /* reserved (iterative refinement of the Newton solve was measured useless and removed) */
     int32_t verbose;         /* 1: device printf of the interior-point iterations (debugging) */
-    int32_t occupancy;       /* CTA kernel variant: 0 auto, 1 = 128 regs/thread, 4 or 8 = 64 regs (min CTAs per SM) */
-    int32_t smem_kb;         /* shared-memory budget per CTA for resident scratch arrays; -1 = auto, 0 = none */
+    int32_t occupancy;       /* CTA kernel variant: 0 auto (2 for large batches, 1 for small), 1 = one 512-thread CTA per SM with
+                                128 regs/thread and resident work vectors, 2 = two 512-thread CTAs per SM (64 regs),
+                                >= 3 = four 256-thread CTAs per SM (64 regs) */
+    int32_t smem_kb;         /* shared-memory budget per CTA for resident work vectors; -1 = auto, 0 = none (the dense tail of
+                                the factor, its inverse diagonal and the solve scratch are always resident) */
 } sqpqp_options;
 
 /* ---- lifecycle ------------------------------------------------------------------ */
