@@ -95,7 +95,7 @@ typedef struct sqpqp_options {
     int32_t ipm_refine;      /* reserved (iterative refinement of the Newton solve was measured useless and removed) */
     int32_t verbose;         /* 1: device printf of the interior-point iterations (debugging) */
     int32_t occupancy;       /* CTA kernel variant: 0 auto (2 for large batches, 1 for small), 1 = one 512-thread CTA per SM with
-                                128 regs/thread and resident work vectors, 2 = two 512-thread CTAs per SM (64 regs),
+                                128 regs/thread and resident work vectors, 2 = two CTAs per SM (384 threads / 80 regs by default, 512 / 64 on request),
                                 >= 3 = four 256-thread CTAs per SM (64 regs) */
     int32_t smem_kb;         /* shared-memory budget per CTA for resident work vectors; -1 = auto, 0 = none (the dense tail of
                                 the factor, its inverse diagonal and the solve scratch are always resident) */

@@ -260,6 +260,8 @@ extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
     cudaFuncSetAttribute(k_solve_cta<512, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem);
     cudaFuncSetAttribute(k_solve_cta<512, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta2_smem);
     cudaFuncSetAttribute(k_solve_cta<512, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta2_smem);
+    cudaFuncSetAttribute(k_solve_cta<384, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta2_smem);
+    cudaFuncSetAttribute(k_solve_cta<384, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta2_smem);
     cudaFuncSetAttribute(k_solve_cta<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta4_smem);
     cudaFuncSetAttribute(k_solve_cta<256, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cta4_smem);
     *out = h;
@@ -825,11 +827,12 @@ static int launch_solve(sqpqp_handle h, int phase) {
         // re-read through L1, so L1 capacity beats vector residency (measured, profiles/r01_tuning.md).
         const bool many = B >= (size_t)2 * h->num_sms;
         int occ = h->opts.occupancy;  // 0 auto
-        // measured (profiles/r01_tuning.md): two 512-thread CTAs per SM beat four 256-thread ones (shorter
-        // per-instance latency for the stragglers of a batch) and one 1024-thread CTA (too little work per phase)
+        // measured (profiles/r01_tuning.md): two CTAs per SM beat four 256-thread ones (shorter per-instance latency for
+        // the stragglers of a batch) and one 1024-thread CTA (too little work per phase); 384 threads (80 registers,
+        // a third of the spills) beat 512 (64 registers) by 3 %
         if (occ == 0) occ = many ? 2 : 1;
         if (!h->opts.threads && many && threads > 256 && occ != 2) threads = 256;
-        if (!h->opts.threads && occ == 2) threads = 512;
+        if (!h->opts.threads && occ == 2) threads = 384;
         bool ipm = (phase == SQPQP_PHASE_FR ? P.has_chol_fr : P.has_chol) && h->opts.method != 1;
         const CholDev& CD = (phase == SQPQP_PHASE_FR) ? P.chol_fr : P.chol;
         size_t budget = occ >= 8 ? 24 * 1024 : (occ >= 3 ? (size_t)h->cta4_smem : (occ == 2 ? (size_t)h->cta2_smem : (size_t)h->max_dyn_smem));
@@ -842,7 +845,7 @@ static int launch_solve(sqpqp_handle h, int phase) {
         place_arrays(P, phase, budget, ipm, vectors, &pl);
         if (ipm && CD.T > 0 && pl.dtail < 0 && occ >= 3) {  // the tail was sized for two CTAs per SM
             occ = 2;
-            if (threads < 512 && !h->opts.threads) threads = 512;
+            if (!h->opts.threads) threads = 384;
             budget = (size_t)h->cta2_smem;
             place_arrays(P, phase, budget, ipm, vectors, &pl);
         }
@@ -855,6 +858,9 @@ static int launch_solve(sqpqp_handle h, int phase) {
             if (cfg == 4) {
                 if (mode == 1) k_solve_cta<256, 4, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
                 else k_solve_cta<256, 4, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+            } else if (cfg == 2 && threads <= 384) {  // 85 registers per thread instead of 64
+                if (mode == 1) k_solve_cta<384, 2, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+                else k_solve_cta<384, 2, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
             } else if (cfg == 2) {
                 if (mode == 1) k_solve_cta<512, 2, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
                 else k_solve_cta<512, 2, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
