@@ -171,6 +171,7 @@ int sqpqp_chol_layout(sqpqp_handle h, int64_t* tail_cols, int64_t* tree_levels);
 int sqpqp_prof_read(sqpqp_handle h, uint64_t* out32);
 /* Development aid: copy a per-instance work array of instance b to the host (kind 0 N-vector slot idx, 1 M-vector
  * slot idx, 2 factor values, 3 solve scratch, 4 inverse diagonal of the factor, 5 weighted Jacobian values). */
+int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value); /* what 0: resident SpMV CTAs per SM */
 int sqpqp_debug_read(sqpqp_handle h, int32_t kind, int32_t idx, int32_t b, double* out, int64_t count);
 /* Number of slack columns S (order: for each row i > m_lin: u_i, then v_i if two-sided). */
 int sqpqp_num_slacks(sqpqp_handle h, int32_t* S);

@@ -82,7 +82,7 @@ EXPORTS = [
     "sqpqp_setup_nlp", "sqpqp_update_nlp", "sqpqp_update_nlp_device", "sqpqp_solve_tr", "sqpqp_num_slacks",
     "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
     "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
-    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read", "sqpqp_linesearch_terms", "sqpqp_acopf_setup", "sqpqp_acopf_eval_update",
+    "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read", "sqpqp_debug_set", "sqpqp_linesearch_terms", "sqpqp_acopf_setup", "sqpqp_acopf_eval_update",
 ]
 
 
@@ -143,6 +143,7 @@ def lib():
                                     C.c_int32, _ip, _ip, _ip, _dp, C.c_int32, _ip]
     L.sqpqp_acopf_eval_update.argtypes = [vp, _dp, _dp, _ip, _dp, _dp, _dp]
     L.sqpqp_linesearch_terms.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+    L.sqpqp_debug_set.argtypes = [vp, C.c_int32, C.c_int32]
     L.sqpqp_debug_read.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_int64]
     L.sqpqp_spmv.argtypes = [vp, C.c_int32, _dp, _dp]
     L.sqpqp_spmv_device.argtypes = [vp, C.c_int32, vp, vp]

@@ -58,6 +58,7 @@ struct sqpqp_handle_s {
     int64_t chol_flops = 0;
     std::vector<double> avg_row;  // avg row length of J(normal), J(ext), T, H
     SpmvPlan planJ{}, planT{}, planH{};
+    int spmv_ctas_per_sm = 8;
     AcopfDev acopf{};       // device-side ACOPF evaluator (acopf.cuh); nb == 0: not set up
     double* d_f = nullptr;  // [batch] objective values of the evaluator  // CSR-stream row blocks of J (normal phase), J' and H
     // generic-lane bookkeeping
@@ -354,6 +355,12 @@ extern "C" int sqpqp_debug_read(sqpqp_handle h, int32_t kind, int32_t idx, int32
     else return fail(h, SQPQP_E_BADARG, "bad selector");
     if ((size_t)count < len) len = (size_t)count;
     CUDA_OK(cudaMemcpy(out, src, len * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value) {  // development knobs
+    if (!h) return SQPQP_E_BADARG;
+    if (what == 0 && value > 0) h->spmv_ctas_per_sm = value;
     return 0;
 }
 
@@ -1063,7 +1070,11 @@ static int launch_spmv(sqpqp_handle h, int which, const double* x, double* y) {
     const SpmvPlan& S = which == 0 ? h->planJ : (which == 1 ? h->planT : h->planH);
     const double* vals = which == 0 ? P.Jv : (which == 1 ? P.Tv : P.Hv);
     if (S.nblocks <= 0 || S.nrows <= 0) return 0;
-    int gy = P.batch < 65535 ? P.batch : 65535;
+    // one CTA per (row block, pair of instances): many short-lived CTAs overlap their load and reduce phases better than
+    // persistent ones (measured: 8 resident CTAs per SM walking the instances reach 1.9 TB/s, this grid 2.5-3.1 TB/s)
+    int gy = (P.batch + SPMV_INST - 1) / SPMV_INST;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
     k_spmv_stream<<<dim3(S.nblocks, gy), SPMV_THREADS, 0, h->stream>>>(S, vals, x, y, which == 1 ? P.m : P.n, P.batch);
     h->launches++;
     CUDA_OK(cudaGetLastError());
