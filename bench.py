@@ -261,7 +261,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spmv", action="store_true", help="skip the 2000-bus SpMV roofline leg")
     ap.add_argument("--no-device-eval", action="store_true", help="skip the full solve with the device-side evaluator")
-    ap.add_argument("--spmv-batch", type=int, default=512)
+    ap.add_argument("--spmv-batch", type=int, default=2048)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
