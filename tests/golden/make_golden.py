@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle.sqp_tr import Parameters, SqpTROracle  # noqa: E402
 from sqpsolver_jl_b200.nlp.acopf import AcopfPolar  # noqa: E402
-from sqpsolver_jl_b200.nlp.networks import case9  # noqa: E402
+from sqpsolver_jl_b200.nlp.networks import case9, synth_net  # noqa: E402
 from sqpsolver_jl_b200.nlp.toy import ReadmeToy, ToyExample  # noqa: E402
 
 CASES = {
@@ -24,12 +24,18 @@ CASES = {
     "readme_toy": (ReadmeToy, dict(max_iter=100)),
     "case9_mu1e4": (lambda: AcopfPolar(case9()), dict(max_iter=100, init_mu=1e4)),
     "case9_default": (lambda: AcopfPolar(case9()), dict(max_iter=60)),
+    # BASELINE configs[2]: the case118-shaped synthetic network, SQP trust-region variant -- the first subproblems only
+    # (the as-coded algorithm does not converge on it within 100 iterations; a fixture of the whole run would be 20 MB)
+    "case118_first": (lambda: AcopfPolar(synth_net(118, 186, 54, 118)), dict(max_iter=6, init_mu=1e5)),
 }
 STATUS_CODE = {"LOCALLY_SOLVED": 4, "INFEASIBLE": 2, "LOCALLY_INFEASIBLE": 5, "ITERATION_LIMIT": 11, "NUMERICAL_ERROR": 20}
 
 if __name__ == "__main__":
     out = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]
     for name, (mk, kw) in CASES.items():
+        if only and name not in only:
+            continue
         trace = []
         s = SqpTROracle(mk(), Parameters(**kw), trace=trace).run()
         keys = ("x", "dE", "h_val", "df", "E", "p", "lambda_qp", "mult_x_U", "mult_x_L", "lam")

@@ -110,7 +110,8 @@ def _scaled_kkt(P, q, A, rl, ru, xl, xu, x, lam, rc):
 
 @pytest.mark.parametrize("name,make", [("toy_example", ToyExample), ("readme_toy", ReadmeToy),
                                        ("case9_mu1e4", lambda: AcopfPolar(case9())),
-                                       ("case9_default", lambda: AcopfPolar(case9()))])
+                                       ("case9_default", lambda: AcopfPolar(case9())),
+                                       ("case118_first", lambda: AcopfPolar(synth_net(118, 186, 54, 118)))])
 def test_qp_subproblems_of_golden_trajectories(engine, name, make):
     """Every QP/FR subproblem of the oracle's SQP trajectory, replayed cold through the C-ABI."""
     g = np.load(os.path.join(GOLD, name + ".npz"))
@@ -156,10 +157,11 @@ def test_qp_subproblems_of_golden_trajectories(engine, name, make):
             n_unique += 1
             dpi = np.abs(p[0] - g["qp_p"][k]).max()  # first-order bound on the objective difference
             assert abs(obj_d - obj_o) <= 1e-6 * max(1.0, abs(obj_o)) + 2.0 * np.abs(q).sum() * dpi
-        elif info[0]["rho_box_floor"] <= 1e-8:
+        elif info[0]["rho_box_floor"] <= 1e-8 and np.linalg.eigvalsh(P.toarray()).min() >= -1e-9 * max(1.0, abs(P).max()):
             # convex QP with a non-unique minimiser (e.g. costless reactive dispatch): same optimal value
             assert abs(obj_d - obj_o) <= 1e-6 * max(1.0, abs(obj_o)), (name, k, obj_d, obj_o)
-        # else: indefinite H -> both are verified KKT points of a nonconvex QP, possibly different ones
+        # else: indefinite H -> both are verified KKT points of a nonconvex QP, possibly different ones (on the
+        # case118-shaped network the device's is the lower one on the subproblems where they differ)
     if name.startswith("case9_mu"):
         assert n_unique >= nq // 2  # most subproblems have one local solution and it must be found
 
