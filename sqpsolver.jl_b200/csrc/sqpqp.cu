@@ -902,7 +902,8 @@ static int launch_solve(sqpqp_handle h, int phase) {
         if (threads > 512) threads = 512;
         if (cfg == 4 && threads > 256) threads = 256;
         if (ipm) launch(1);
-        else CUDA_OK(cudaMemsetAsync(P.fb_flag, 0, B * sizeof(int), h->stream));
+        else CUDA_OK(cudaMemsetAsync(P.fb_flag, 1, B * sizeof(int), h->stream));  // no factorisation available: every instance
+                                                                                  // is "flagged" (non-zero) for the ADMM launch
         if (h->opts.method != 2) launch(2);
         h->launches--;  // counted below
     }

@@ -205,6 +205,29 @@ def test_generic_qp_lane_strictly_convex_matches_oracle(engine):
         assert np.abs(cd - res.col_dual).max() <= 1e-6 * max(1.0, np.abs(res.col_dual).max()), msg
 
 
+def test_admm_path_when_no_factorisation_is_available(engine):
+    """A constraint row longer than the clique expansion allows (600 > 512 entries) leaves the engine without a symbolic
+    Cholesky: the auto method must then run the ADMM + PCG + polish kernel for every instance (the north-star algorithm),
+    not silently do nothing.  Strictly convex QP -> unique solution, compared with the oracle."""
+    rng = np.random.default_rng(5)
+    n = 600
+    A = sp.coo_matrix(np.vstack([np.ones((1, n)), sp.random(3, n, 0.02, random_state=1).toarray()]))
+    d = rng.uniform(1.0, 2.0, n)
+    q = rng.standard_normal(n)
+    rl, ru = np.array([1.0, -0.5, -0.5, -0.5]), np.array([1.0, 0.5, 0.5, 0.5])
+    cl, cu = np.full(n, -0.2), np.full(n, 0.2)
+    idx = np.arange(n)
+    engine.qp_setup(n, 4, idx + 1, idx + 1, A.row + 1, A.col + 1)
+    assert engine.chol_stats()["nnzL"] == 0
+    x, rd, cd, st, info = engine.qp_solve(d, q, A.data, rl, ru, cl, cu)
+    assert st in OK and info["admm_iters"] > 0 and info["ipm_iters"] == 0, (st, info)
+    res = qs.solve_qp(sp.diags(d).tocsr(), q, A.tocsr(), rl, ru, cl, cu)
+    assert res.status in qs.OK_STATUSES
+    # first-order method: the north-star bar is the scaled KKT residual (1e-6); the minimiser itself to 1e-5
+    assert _scaled_kkt(sp.diags(d).tocsr(), q, A.tocsr(), rl, ru, cl, cu, x, rd, cd) <= 1e-6
+    assert np.abs(x - res.x).max() <= 1e-5 * max(1.0, np.abs(res.x).max())
+
+
 def test_lp_projection_phase(engine):
     """sub_optimize_lp (subproblem_JuMP.jl:185-244): nearest point to x_k on linear rows + bounds."""
     nlp = AcopfPolar(case9())
