@@ -259,7 +259,12 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
             chol_assemble(T, C, W, I.useH ? I.Hsv : (const double*)nullptr, I.nv[N_DSH], rho_p, I.mv[M_RW], I.Jsv, pf);
             fact_ok = chol_factor(T, C, W, pf);
             ++out.nfact;
-            if (!fact_ok) rho_p = fmax(fmax(10.0 * rho_p, rho_last > 0.0 ? rho_last / 3.0 : 1e-4), 1e-6);
+            // Growth 4 on a failed factorisation (the shift decays by 3 per iteration, so this returns to just above the
+            // last value that worked).  The textbook 8-10 overshoots on the indefinite ACOPF subproblems: the extra
+            // regularisation shortens the Newton steps, the shift decays, fails and overshoots again -- the six slowest
+            // recorded subproblems need 228 iterations / 330 factorisations in total with 4 against 504 / 712 with 10
+            // (profiles/r01_tuning.md section 6).
+            if (!fact_ok) rho_p = fmax(fmax(4.0 * rho_p, rho_last > 0.0 ? rho_last / 3.0 : 1e-4), 1e-6);
             if (rho_p > 1e8) break;
         }
         if (!fact_ok) break;
