@@ -1,7 +1,7 @@
 """DEVELOPMENT TOOL: 2000-bus instance, start-point projection and first QP on the device vs the CPU oracle."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from sqpsolver_jl_b200 import capi
 from sqpsolver_jl_b200.nlp.networks import synth_net
 from sqpsolver_jl_b200.nlp.acopf import AcopfPolar

@@ -1,7 +1,7 @@
 """DEVELOPMENT TOOL: first-light checks of the CUDA engine on a GPU box (run under gpurun)."""
 import sys, os, time, pickle
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from sqpsolver_jl_b200 import capi
 from sqpsolver_jl_b200.nlp.networks import case9, synth_net
 from sqpsolver_jl_b200.nlp.acopf import AcopfPolar

@@ -1,7 +1,7 @@
 """DEVELOPMENT TOOL: generic-lane random convex QP with verbose IPM trace."""
 import os, sys
 import numpy as np, scipy.sparse as sp
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from sqpsolver_jl_b200 import capi
 from oracle import qp_solver as qs
 rng = np.random.default_rng(21)

@@ -1,7 +1,7 @@
 """DEVELOPMENT TOOL: device status on the oracle-infeasible QPs of the case9_default golden trajectory."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from sqpsolver_jl_b200 import capi
 from sqpsolver_jl_b200.nlp.acopf import AcopfPolar
 from sqpsolver_jl_b200.nlp.networks import case9

@@ -1,7 +1,7 @@
 """DEVELOPMENT TOOL: device line-search driver next to its CPU restatement."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from sqpsolver_jl_b200.nlp.networks import case9
 from sqpsolver_jl_b200.nlp.acopf import AcopfPolar
 from sqpsolver_jl_b200.nlp.toy import ToyExample, ReadmeToy

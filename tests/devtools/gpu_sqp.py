@@ -1,7 +1,7 @@
 """DEVELOPMENT TOOL: run the device-backed SQP-TR driver next to the oracle (under gpurun)."""
 import sys, os, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from sqpsolver_jl_b200.nlp.networks import case9, synth_net
 from sqpsolver_jl_b200.nlp.acopf import AcopfPolar
 from sqpsolver_jl_b200.nlp.toy import ToyExample, ReadmeToy

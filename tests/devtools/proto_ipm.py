@@ -37,6 +37,7 @@ class Opts:
     rho_hold = 0       # iterations the shift is held after a failed factorisation
     rho_floor_frac = 0.0  # never decay below this fraction of the last shift that was NEEDED
     mu_force = 0       # force a barrier decrease after this many iterations without one (0 = never)
+    loqo = False       # LOQO-style adaptive barrier parameter instead of the monotone rule
 
 
 class _SymLU:
@@ -199,6 +200,11 @@ def ipm_solve(P, q, J, rl, ru, xl, xu, o: Opts = Opts()):
                 if o.mu_force and stall >= o.mu_force and mu_t > 1e-13:
                     mu_t = max(1e-13, 0.2 * mu_t)
                     stall = 0
+            if o.loqo:
+                prods = np.concatenate([(s * z)[mk] for s, z, mk in zip(S, Z, MK)])
+                avg = prods.mean(); xi = prods.min() / avg
+                sig = 0.1 * min(0.05 * (1 - xi) / max(xi, 1e-12), 2.0) ** 3
+                mu_t = max(1e-13, sig * avg)
             rc = [mu_t - s * z for s, z in zip(S, Z)]
             dx, dZ, dS, dy, dyx = solve_dir(*rc)
             tau = max(o.tau, 1.0 - mu_t)
