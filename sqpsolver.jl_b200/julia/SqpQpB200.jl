@@ -86,6 +86,39 @@ function sub_optimize_lp(qp::QpDevice, x_k)                                   # 
     return x, λ, mxU, mxL, st
 end
 
+# The arithmetic around each QP solve, on the device matrices of the last update!
+"norm_violations / compute_phi / compute_qmodel (common.jl:54-77, sqp.jl:170-183, sqp_trust_region.jl:487-508)"
+function merit(qp::QpDevice, x, p, E_trial, f_trial::Float64, μ::Float64, fr::Bool)
+    o = [Ref(0.0) for _ in 1:5]
+    check(qp.h, ccall((:sqpqp_merit, libsqpqp), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Float64}, Ref{Int32},
+         Ref{Float64}, Ref{Float64}, Ref{Float64}, Ref{Float64}, Ref{Float64}),
+        qp.h, x, p, E_trial, f_trial, μ, Int32(fr), o[1], o[2], o[3], o[4], o[5]))
+    return (viol0 = o[1][], viol_trial = o[2][], phi_trial = o[3][], q0 = o[4][], qk = o[5][])
+end
+"KT_residuals (common.jl:14-23), as coded"
+function kt_residuals(qp::QpDevice, λ, mult_x_U, mult_x_L)
+    kt = Ref(0.0)
+    check(qp.h, ccall((:sqpqp_kt_residuals, libsqpqp), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}), qp.h, λ, mult_x_U, mult_x_L, kt))
+    return kt[]
+end
+"which = 0: Jacobian * x, 1: Jacobian' * x, 2: Hessian * x (sqp_trust_region.jl:343,490,492, common.jl:17)"
+function spmv(qp::QpDevice, which::Integer, x::Vector{Float64})
+    y = zeros(which == 0 ? qp.m : qp.n)
+    check(qp.h, ccall((:sqpqp_spmv, libsqpqp), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}), qp.h, which, x, y))
+    return y
+end
+"line-search merit primitives (sqp_line_search.jl:271-334, sqp.jl:190-213, merit.jl:13-17, common.jl:30-47)"
+function linesearch_terms(qp::QpDevice, x, p, α::Float64, E_trial, μ_rows, λ)
+    out = zeros(8)
+    check(qp.h, ccall((:sqpqp_linesearch_terms, libsqpqp), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        qp.h, x, p, α, E_trial, μ_rows, λ, out))
+    return (dfp = out[1], pHp = out[2], viol1 = out[3], violinf = out[4], wviol0 = out[5], wviol_trial = out[6],
+            viol1_trial = out[7], compl = out[8])
+end
+
 # ------------------------------------------------------------------------------------------
 # B1: generic MOI optimizer (copy_to based)
 # ------------------------------------------------------------------------------------------
