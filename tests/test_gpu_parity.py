@@ -318,6 +318,54 @@ def test_batched_instances_match_individual_oracle_runs(built_lib):
     bt.close()
 
 
+@pytest.mark.parametrize("indefinite", [False, True])
+def test_full_size_batch_kkt_property(built_lib, indefinite):
+    """BASELINE configs[4] at full size (1024 perturbed-load case118-shaped instances, one shared pattern): every
+    subproblem of the batch must be a KKT point of ITS OWN data to 1e-6 (scaled) -- the size-independent property of the
+    path; four sampled instances are additionally compared with the oracle.  `indefinite` evaluates the Hessian of the
+    Lagrangian with large random multipliers, which makes the QPs nonconvex (inertia correction path)."""
+    B = 1024
+    net = synth_net(118, 186, 54, seed=118)
+    pd, qd = net.perturbed_loads(B)
+    nlp = AcopfPolar(net, pd=pd, qd=qd)
+    rng = np.random.default_rng(3)
+    x = np.clip(np.broadcast_to(nlp.x0, (B, nlp.n)) + 0.02 * rng.standard_normal((B, nlp.n)), nlp.x_L, nlp.x_U)
+    lam = 50.0 * rng.standard_normal((B, nlp.m)) if indefinite else np.zeros((B, nlp.m))
+    df = np.empty((B, nlp.n)); nlp.eval_grad_f(x, df)
+    E = np.empty((B, nlp.m)); nlp.eval_g(x, E)
+    dE = np.empty((B, nlp.nnz_jac_coo)); nlp.eval_jac_g(x, dE)
+    hv = np.empty((B, nlp.nnz_hess_coo)); nlp.eval_h(x, 1.0, lam, hv)
+    eng = capi.Engine()
+    try:
+        _setup(eng, nlp, batch=B)
+        eng.update_nlp(dE, hv, df, E)
+        Delta = 2.0 if indefinite else 10.0
+        p, mult, mxL, mxU, _, st, info = eng.solve_tr(capi.PHASE_QP, x, Delta)
+    finally:
+        eng.close()
+    ok = np.isin(st, OK)
+    assert ok.mean() >= 0.99, np.unique(st, return_counts=True)
+    assert np.isin(st[~ok], (capi.MOI_INFEASIBLE, capi.MOI_LOCALLY_INFEASIBLE)).all()
+    J = CooMatrix(nlp.j_row, nlp.j_col, nlp.m, nlp.n)
+    H = SymCooMatrix(nlp.h_row, nlp.h_col, nlp.n)
+    gL = nlp.g_L if nlp.g_L.ndim == 2 else np.broadcast_to(nlp.g_L, (B, nlp.m))
+    gU = nlp.g_U if nlp.g_U.ndim == 2 else np.broadcast_to(nlp.g_U, (B, nlp.m))
+    worst = 0.0
+    for b in np.nonzero(ok)[0]:
+        J.fill(dE[b]); H.fill(hv[b])
+        lb, ub = trust_region_box(nlp.x_L - x[b], nlp.x_U - x[b], Delta)
+        worst = max(worst, _scaled_kkt(H.to_scipy(), df[b], J.to_scipy(), gL[b] - E[b], gU[b] - E[b], lb, ub, p[b], mult[b],
+                                       mxL[b] + mxU[b]))
+    assert worst <= 1e-6, worst
+    if not indefinite:  # convex: the optimal value is unique
+        for b in (0, 341, 682, 1023):
+            J.fill(dE[b]); H.fill(hv[b])
+            lb, ub = trust_region_box(nlp.x_L - x[b], nlp.x_U - x[b], Delta)
+            res = qs.solve_qp(H.to_scipy(), df[b], J.to_scipy(), gL[b] - E[b], gU[b] - E[b], lb, ub)
+            obj = 0.5 * p[b] @ (H.to_scipy() @ p[b]) + df[b] @ p[b]
+            assert abs(obj - res.obj) <= 1e-6 * max(1.0, abs(res.obj)), (b, obj, res.obj)
+
+
 @pytest.mark.parametrize("make", [lambda: AcopfPolar(case9()), lambda: AcopfPolar(synth_net(118, 186, 54, 118)),
                                   lambda: AcopfPolar(synth_net(2000, 3000, 400, 2000))])
 def test_batched_spmv_bit_exact_against_sequential_csr(engine, make):
