@@ -203,6 +203,10 @@ class Engine:
         self.opts = Options()
         self.L.sqpqp_default_options(C.byref(self.opts))
         self.batch = self.n = self.m = self.S = 0
+        # True: solve_tr writes into one persistent set of result arrays (valid until the next call) instead of
+        # allocating new ones -- what a host that owns its result buffers (the Julia shim, bench.py's e2e leg) does
+        self.reuse_outputs = False
+        self._out = None
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
@@ -264,13 +268,20 @@ class Engine:
         delta = np.ascontiguousarray(np.broadcast_to(np.asarray(delta, dtype=np.float64), (B,)))
         E_override = _f64(E_override).reshape(B, m) if E_override is not None else None
         act = np.ascontiguousarray(active, dtype=np.int32).reshape(B) if active is not None else None
-        p = np.zeros((B, n))
-        lam = np.zeros((B, m))
-        mxL = np.zeros((B, n))
-        mxU = np.zeros((B, n))
-        slack = np.zeros((B, max(S, 1)))
-        status = np.zeros(B, dtype=np.int32)
-        info = np.zeros(B, dtype=INFO_DTYPE)
+        if self.reuse_outputs and self._out is not None and self._out[0].shape == (B, n) and self._out[1].shape == (B, m):
+            # caller-owned result buffers, as a compiled host would pass to the C ABI: the arrays returned by the
+            # previous call are overwritten (fresh 60 MB numpy arrays cost ~6 ms of page faults per call at batch 1024)
+            p, lam, mxL, mxU, slack, status, info = self._out
+        else:
+            p = np.zeros((B, n))
+            lam = np.zeros((B, m))
+            mxL = np.zeros((B, n))
+            mxU = np.zeros((B, n))
+            slack = np.zeros((B, max(S, 1)))
+            status = np.zeros(B, dtype=np.int32)
+            info = np.zeros(B, dtype=INFO_DTYPE)
+            if self.reuse_outputs:
+                self._out = (p, lam, mxL, mxU, slack, status, info)
         self._ck(self.L.sqpqp_solve_tr(self.h, phase, _d(x_k), _d(delta), _d(E_override), _i(act), _d(p), _d(lam), _d(mxL),
                                        _d(mxU), _d(slack), _i(status), info.ctypes.data_as(C.c_void_p)))
         return p, lam, mxL, mxU, slack[:, :S], status, info

@@ -26,6 +26,7 @@ struct Pending {
     const void* pin;
     void* user;
     size_t bytes;
+    cudaEvent_t ev;  // recorded behind the D2H copy of a large item (null: wait for the stream)
 };
 
 struct sqpqp_handle_s {
@@ -43,6 +44,8 @@ struct sqpqp_handle_s {
     char* dstage = nullptr;
     size_t stage_cap = 0, stage_off = 0;
     std::vector<Pending> pending;
+    std::vector<cudaEvent_t> evpool;  // per-item completion events of the staged downloads
+    size_t ev_used = 0;
     // scatter
     ScatterJob jobJ{}, jobT{}, jobH{};
     double *d_dE = nullptr, *d_hval = nullptr, *d_df = nullptr, *d_E = nullptr;  // owned copies
@@ -119,18 +122,21 @@ static int ensure_stage(sqpqp_handle h, size_t bytes) {
     }
     h->stage_off = 0;
     h->pending.clear();
+    h->ev_used = 0;
     return 0;
 }
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // host -> pinned -> device (async).  Returns device pointer inside the staging mirror.
 // Host-side copy between caller memory and the pinned staging area.  Above a few MB one thread cannot feed PCIe
-// (~8 GB/s single-threaded memcpy against ~50 GB/s H2D): split the copy over a few threads.
+// (~8 GB/s single-threaded memcpy): split the copy over a few threads.  Measured on the B200 box (tools/
+// gpu_e2e_breakdown.py): 134 MB of update_nlp inputs take 6.4 ms = 21 GB/s whatever the piece size and thread count
+// (2..14 threads, 16 MB..whole array) -- the link, not the staging copy, is the floor.
 static void par_memcpy(void* dst, const void* src, size_t bytes) {
-    const size_t kMin = (size_t)4 << 20;
+    const size_t kMin = (size_t)2 << 20, kMaxT = 8;
     unsigned hw = std::thread::hardware_concurrency();
     size_t nt = bytes / kMin;
-    if (nt > 8) nt = 8;
+    if (nt > kMaxT) nt = kMaxT;
     if (hw && nt > hw) nt = hw;
     if (nt < 2) { memcpy(dst, src, bytes); return; }
     std::vector<std::thread> th;
@@ -145,17 +151,30 @@ static void par_memcpy(void* dst, const void* src, size_t bytes) {
     for (auto& x : th) x.join();
 }
 
+// Staged host -> device copy, pipelined: the caller's buffer is copied into the pinned area in pieces and every piece
+// starts its H2D transfer as soon as it is staged, so the transfer overlaps the host copy of the next piece.
+static const size_t kStagePiece = (size_t)32 << 20;
+static cudaError_t stage_h2d(sqpqp_handle h, void* ddst, size_t pin_off, const void* src, size_t bytes) {
+    for (size_t o = 0; o < bytes; o += kStagePiece) {
+        const size_t len = bytes - o < kStagePiece ? bytes - o : kStagePiece;
+        par_memcpy(h->pin + pin_off + o, (const char*)src + o, len);
+        cudaError_t e = cudaMemcpyAsync((char*)ddst + o, h->pin + pin_off + o, len, cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 template <class T>
 static const T* upload(sqpqp_handle h, const T* src, size_t count) {
     if (!src || count == 0) return nullptr;
     size_t bytes = count * sizeof(T);
     size_t off = h->stage_off;
     h->stage_off = align256(off + bytes);
-    par_memcpy(h->pin + off, src, bytes);
-    cudaMemcpyAsync(h->dstage + off, h->pin + off, bytes, cudaMemcpyHostToDevice, h->stream);
+    stage_h2d(h, h->dstage + off, off, src, bytes);
     return (const T*)(h->dstage + off);
 }
-// device -> pinned (async) and remember the final host copy
+// device -> pinned (async) and remember the final host copy; large items get their own completion event so that
+// finish() can copy item k to the caller while item k+1 is still crossing PCIe
 template <class T>
 static void download(sqpqp_handle h, const T* dsrc, T* user, size_t count) {
     if (!user || count == 0) return;
@@ -163,12 +182,30 @@ static void download(sqpqp_handle h, const T* dsrc, T* user, size_t count) {
     size_t off = h->stage_off;
     h->stage_off = align256(off + bytes);
     cudaMemcpyAsync(h->pin + off, dsrc, bytes, cudaMemcpyDeviceToHost, h->stream);
-    h->pending.push_back(Pending{h->pin + off, user, bytes});
+    cudaEvent_t ev = nullptr;
+    if (bytes >= ((size_t)1 << 20)) {
+        if (h->ev_used == h->evpool.size()) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) h->evpool.push_back(e);
+        }
+        if (h->ev_used < h->evpool.size()) {
+            ev = h->evpool[h->ev_used++];
+            cudaEventRecord(ev, h->stream);
+        }
+    }
+    h->pending.push_back(Pending{h->pin + off, user, bytes, ev});
 }
 static int finish(sqpqp_handle h) {
+    for (auto& p : h->pending)
+        if (p.ev) {
+            CUDA_OK(cudaEventSynchronize(p.ev));
+            par_memcpy(p.user, p.pin, p.bytes);
+        }
     CUDA_OK(cudaStreamSynchronize(h->stream));
-    for (auto& p : h->pending) par_memcpy(p.user, p.pin, p.bytes);
+    for (auto& p : h->pending)
+        if (!p.ev) par_memcpy(p.user, p.pin, p.bytes);
     h->pending.clear();
+    h->ev_used = 0;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -307,6 +344,7 @@ extern "C" int sqpqp_destroy(sqpqp_handle h) {
     if (h->dstage) cudaFree(h->dstage);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (auto e : h->evpool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -678,8 +716,7 @@ extern "C" int sqpqp_update_nlp(sqpqp_handle h, const double* dE, const double* 
         if (!c.cnt) continue;
         size_t off = h->stage_off;
         h->stage_off = align256(off + c.cnt * sizeof(double));
-        par_memcpy(h->pin + off, c.src, c.cnt * sizeof(double));
-        CUDA_OK(cudaMemcpyAsync(c.dst, h->pin + off, c.cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CUDA_OK(stage_h2d(h, c.dst, off, c.src, c.cnt * sizeof(double)));
     }
     P.df = h->d_df; P.E = h->d_E;
     launch_scatter(h, h->d_dE, h->d_hval);
