@@ -38,6 +38,10 @@ class Opts:
     rho_floor_frac = 0.0  # never decay below this fraction of the last shift that was NEEDED
     mu_force = 0       # force a barrier decrease after this many iterations without one (0 = never)
     loqo = False       # LOQO-style adaptive barrier parameter instead of the monotone rule
+    split_step = False # separate primal and dual step lengths (Ipopt) instead of one common step
+    sigma_rule = 0.0   # > 0: barrier target = sigma * current average complementarity, every iteration
+    kappa_mu = 0.2     # linear / superlinear decrease of the barrier parameter (Ipopt: 0.2, 1.5)
+    theta_mu = 1.5
 
 
 class _SymLU:
@@ -190,7 +194,7 @@ def ipm_solve(P, q, J, rl, ru, xl, xu, o: Opts = Opts()):
                 comp = max(_ninf((s * z - mu_t) * mk) for s, z, mk in zip(S, Z, MK))
                 e_mu = max(rd * c if False else _ninf(r_x), _ninf(r_eq), _ninf(r_ru), _ninf(r_rl), _ninf(r_eqx), _ninf(r_xu), _ninf(r_xl), comp)
                 if e_mu <= o.kappa_eps * mu_t and mu_t > 1e-13:
-                    mu_t = max(1e-13, min(0.2 * mu_t, mu_t ** 1.5))
+                    mu_t = max(1e-13, min(o.kappa_mu * mu_t, mu_t ** o.theta_mu))
                 else:
                     break
             if mu_t < mu_before:
@@ -205,13 +209,19 @@ def ipm_solve(P, q, J, rl, ru, xl, xu, o: Opts = Opts()):
                 avg = prods.mean(); xi = prods.min() / avg
                 sig = 0.1 * min(0.05 * (1 - xi) / max(xi, 1e-12), 2.0) ** 3
                 mu_t = max(1e-13, sig * avg)
+            if o.sigma_rule > 0.0:
+                mu_t = max(1e-13, o.sigma_rule * mu)
             rc = [mu_t - s * z for s, z in zip(S, Z)]
             dx, dZ, dS, dy, dyx = solve_dir(*rc)
             tau = max(o.tau, 1.0 - mu_t)
             a = min(1.0, tau * min(max_step(S, dS, MK), max_step(Z, dZ, MK)))
-            x = x + a * dx; y = y + a * dy; yx = yx + a * dyx
+            ad = a
+            if o.split_step:
+                a = min(1.0, tau * max_step(S, dS, MK)); ad = min(1.0, tau * max_step(Z, dZ, MK))
+            x = x + a * dx; y = y + ad * dy; yx = yx + ad * dyx
             s_ru, s_rl, s_xu, s_xl = [s + a * ds for s, ds in zip(S, dS)]
-            z_ru, z_rl, z_xu, z_xl = [z + a * dz for z, dz in zip(Z, dZ)]
+            z_ru, z_rl, z_xu, z_xl = [z + ad * dz for z, dz in zip(Z, dZ)]
+            if o.verbose: print(f"      alpha_p={a:.3f} alpha_d={ad:.3f} mu_t={mu_t:.2e}")
             delta = max(o.delta_min, delta * 0.3)
             if hold > 0:
                 hold -= 1
