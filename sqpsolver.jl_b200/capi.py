@@ -204,7 +204,7 @@ class Engine:
         self.L.sqpqp_default_options(C.byref(self.opts))
         self.batch = self.n = self.m = self.S = 0
         # True: solve_tr writes into one persistent set of result arrays (valid until the next call) instead of
-        # allocating new ones -- what a host that owns its result buffers (the Julia shim, bench.py's e2e leg) does
+        # allocating new ones -- for a batched host that owns its result buffers (bench.py's e2e leg)
         self.reuse_outputs = False
         self._out = None
 
@@ -268,7 +268,8 @@ class Engine:
         delta = np.ascontiguousarray(np.broadcast_to(np.asarray(delta, dtype=np.float64), (B,)))
         E_override = _f64(E_override).reshape(B, m) if E_override is not None else None
         act = np.ascontiguousarray(active, dtype=np.int32).reshape(B) if active is not None else None
-        if self.reuse_outputs and self._out is not None and self._out[0].shape == (B, n) and self._out[1].shape == (B, m):
+        if (self.reuse_outputs and self._out is not None and self._out[0].shape == (B, n) and self._out[1].shape == (B, m)
+                and self._out[4].shape == (B, max(S, 1))):
             # caller-owned result buffers, as a compiled host would pass to the C ABI: the arrays returned by the
             # previous call are overwritten (fresh 60 MB numpy arrays cost ~6 ms of page faults per call at batch 1024)
             p, lam, mxL, mxU, slack, status, info = self._out
