@@ -465,8 +465,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload (first QP
                          # round, 1024 instances) from the ncu --set full capture summarised in profiles/r01_ncu_summary_v2.md
-                         # section 4; a recorded measurement, not re-measured by this run (null when the shard differs)
-                         "traffic": 40.9e9 if (Bl == 1024 and args.workload == "batch118") else None,
+                         # section 6 (final build, k_solve_cta<384,2,1>); a recorded measurement, not re-measured by this run (null when the shard differs)
+                         "traffic": 36.1e9 if (Bl == 1024 and args.workload == "batch118") else None,
                          "traffic_algorithmic_bytes_same_launch": 25.0e9 if (Bl == 1024 and args.workload == "batch118") else None,
                          "kernel": "k_solve_cta<512,2,1>",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",

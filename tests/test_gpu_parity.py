@@ -577,6 +577,26 @@ def test_solve_is_bit_reproducible(engine):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[6][0]["cg_iters"] == b[6][0]["cg_iters"]
 
 
+def test_caller_owned_result_buffers(engine):
+    """`Engine.reuse_outputs`: the same arrays come back on every call and hold the same bits as freshly allocated ones
+    (the staged, per-array pipelined download of the C ABI writes whole arrays)."""
+    g = np.load(os.path.join(GOLD, "case9_mu1e4.npz"))
+    nlp = AcopfPolar(case9())
+    _setup(engine, nlp)
+    engine.set_options(warm_start=0)
+    engine.update_nlp(g["qp_dE"][3], g["qp_h_val"][3], g["qp_df"][3], g["qp_E"][3])
+    fresh = engine.solve_tr(capi.PHASE_QP, g["qp_x"][3], g["qp_Delta"][3])
+    engine.reuse_outputs = True
+    a = engine.solve_tr(capi.PHASE_QP, g["qp_x"][3], g["qp_Delta"][3])
+    keep = [v.copy() for v in a[:6]]
+    engine.update_nlp(g["qp_dE"][5], g["qp_h_val"][5], g["qp_df"][5], g["qp_E"][5])
+    b = engine.solve_tr(capi.PHASE_QP, g["qp_x"][5], g["qp_Delta"][5])
+    assert all(x is y or x.base is y.base for x, y in zip(a[:4], b[:4]))  # same buffers, overwritten
+    assert all(np.array_equal(x, y) for x, y in zip(keep, fresh[:6]))
+    assert not np.array_equal(b[0], keep[0])
+    engine.reuse_outputs = False
+
+
 def test_error_paths(engine):
     import ctypes as C
     rc = engine.L.sqpqp_update_nlp(engine.h, None, None, None, None)  # update before setup
