@@ -468,7 +468,8 @@ def main():
                          # section 6 (final build, k_solve_cta<384,2,1>); a recorded measurement, not re-measured by this run (null when the shard differs)
                          "traffic": 36.1e9 if (Bl == 1024 and args.workload == "batch118") else None,
                          "traffic_algorithmic_bytes_same_launch": 25.0e9 if (Bl == 1024 and args.workload == "batch118") else None,
-                         "kernel": "k_solve_cta<512,2,1>",
+                         # launch shape chosen by launch_solve (csrc/sqpqp.cu): two 384-thread CTAs per SM from 2 x 148 instances up
+                         "kernel": "k_solve_cta<384,2,1>" if Bl >= 296 else "k_solve_cta<512,1,1>",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "note": "achieved = algorithmic bytes / CUDA-event duration of the solve kernel; bytes = per-instance fp64 values each "
                                  "phase of an interior-point iteration must touch once (%d B per iteration + %d B per Cholesky factorisation, "
