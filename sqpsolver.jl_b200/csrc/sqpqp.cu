@@ -53,6 +53,8 @@ struct sqpqp_handle_s {
     double *d_xk = nullptr, *d_delta = nullptr, *d_Eov = nullptr;
     int* d_active = nullptr;
     int64_t launches = 0;
+    cudaError_t async_err = cudaSuccess;  // first failure of a staged copy (upload / download); reported by finish() / the caller
+    int tail_override = -1;               // development knob (sqpqp_debug_set what = 1): cap of the dense tail in columns
     double last_ms = 0.0;
     bool timing_pending = false;
     int num_sms = 148, coop_blocks = 0, max_dyn_smem = 0;
@@ -123,6 +125,7 @@ static int ensure_stage(sqpqp_handle h, size_t bytes) {
     h->stage_off = 0;
     h->pending.clear();
     h->ev_used = 0;
+    h->async_err = cudaSuccess;
     return 0;
 }
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -169,8 +172,13 @@ static const T* upload(sqpqp_handle h, const T* src, size_t count) {
     if (!src || count == 0) return nullptr;
     size_t bytes = count * sizeof(T);
     size_t off = h->stage_off;
+    if (off + bytes > h->stage_cap) {  // the caller sized the staging area too small: never write past it
+        if (h->async_err == cudaSuccess) h->async_err = cudaErrorInvalidValue;
+        return nullptr;
+    }
     h->stage_off = align256(off + bytes);
-    stage_h2d(h, h->dstage + off, off, src, bytes);
+    cudaError_t e = stage_h2d(h, h->dstage + off, off, src, bytes);
+    if (e != cudaSuccess && h->async_err == cudaSuccess) h->async_err = e;
     return (const T*)(h->dstage + off);
 }
 // device -> pinned (async) and remember the final host copy; large items get their own completion event so that
@@ -180,8 +188,13 @@ static void download(sqpqp_handle h, const T* dsrc, T* user, size_t count) {
     if (!user || count == 0) return;
     size_t bytes = count * sizeof(T);
     size_t off = h->stage_off;
+    if (off + bytes > h->stage_cap) {
+        if (h->async_err == cudaSuccess) h->async_err = cudaErrorInvalidValue;
+        return;
+    }
     h->stage_off = align256(off + bytes);
-    cudaMemcpyAsync(h->pin + off, dsrc, bytes, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t ce = cudaMemcpyAsync(h->pin + off, dsrc, bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (ce != cudaSuccess && h->async_err == cudaSuccess) h->async_err = ce;
     cudaEvent_t ev = nullptr;
     if (bytes >= ((size_t)1 << 20)) {
         if (h->ev_used == h->evpool.size()) {
@@ -196,6 +209,14 @@ static void download(sqpqp_handle h, const T* dsrc, T* user, size_t count) {
     h->pending.push_back(Pending{h->pin + off, user, bytes, ev});
 }
 static int finish(sqpqp_handle h) {
+    if (h->async_err != cudaSuccess) {  // a staged copy of this call failed: report it instead of handing back stale data
+        cudaError_t e = h->async_err;
+        h->async_err = cudaSuccess;
+        cudaStreamSynchronize(h->stream);
+        h->pending.clear();
+        h->ev_used = 0;
+        return fail_cuda(h, e, "staged host<->device copy", __LINE__);
+    }
     for (auto& p : h->pending)
         if (p.ev) {
             CUDA_OK(cudaEventSynchronize(p.ev));
@@ -403,6 +424,7 @@ extern "C" int sqpqp_debug_read(sqpqp_handle h, int32_t kind, int32_t idx, int32
     if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
     DeviceGuard g(h->device);
     Prob& P = h->P;
+    if (b < 0 || b >= P.batch) return fail(h, SQPQP_E_BADARG, "instance index out of range");
     CUDA_OK(cudaStreamSynchronize(h->stream));
     const double* src = nullptr;
     size_t len = 0;
@@ -421,6 +443,7 @@ extern "C" int sqpqp_debug_read(sqpqp_handle h, int32_t kind, int32_t idx, int32
 extern "C" int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value) {  // development knobs
     if (!h) return SQPQP_E_BADARG;
     if (what == 0 && value > 0) h->spmv_ctas_per_sm = value;
+    if (what == 1) h->tail_override = value;
     return 0;
 }
 
@@ -475,6 +498,13 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             ssign.push_back(-1.0);
         }
     }
+    if (bounds_per_instance)  // the slack-column structure is shared by the batch: every instance must have the finiteness
+        for (int b = 1; b < batch; ++b)  // pattern of instance 0 on the nonlinear rows (a different one would silently get a wrong FR model)
+            for (int i = m_lin; i < m; ++i) {
+                const double l0 = g_L[i], u0 = g_U[i], lb = g_L[(size_t)b * m + i], ub = g_U[(size_t)b * m + i];
+                if ((l0 > -INFINITY) != (lb > -INFINITY) || (u0 < INFINITY) != (ub < INFINITY))
+                    return fail(h, SQPQP_E_BADARG, "instances of a batch must share the finite/infinite pattern of g_L, g_U on the nonlinear rows");
+            }
     const int S = (int)srow.size();
     P.S = S;
     P.Ne = n + S;
@@ -616,7 +646,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         // (no CTA-local shared memory across the team) and keeps the plain level-scheduled code.
         auto tail_cap = [&](int ncols) -> int {
             if (batch == 1 && (size_t)P.Ne + m > 6000) return 0;
-            if (const char* ev = getenv("SQPQP_TAIL_MAX")) return atoi(ev);  // development override
+            if (h->tail_override >= 0) return h->tail_override;  // sqpqp_debug_set(h, 1, columns): tuning runs only
             size_t cap = (size_t)h->cta2_smem / sizeof(double);
             size_t vec = 2 * (size_t)((ncols + 1) & ~1);
             if (vec <= cap / 2) cap -= vec;
@@ -891,7 +921,9 @@ static int launch_solve(sqpqp_handle h, int phase) {
         // work vectors and matrix values only when one CTA owns the SM (small batches).  Large batches:
         // several CTAs share an SM and hide each other's latency, and the shared index programs are
         // re-read through L1, so L1 capacity beats vector residency (measured, profiles/r01_tuning.md).
-        const bool many = B >= (size_t)2 * h->num_sms;
+        // more instances than SMs: two CTAs per SM, so that up to 2 x num_sms instances are co-resident in ONE wave (with
+        // one CTA per SM a shard of 149..295 instances ran as one full wave plus a partial one: the N = 4 cliff of round 1)
+        const bool many = B > (size_t)h->num_sms;
         int occ = h->opts.occupancy;  // 0 auto
         // measured (profiles/r01_tuning.md): two CTAs per SM beat four 256-thread ones (shorter per-instance latency for
         // the stragglers of a batch) and one 1024-thread CTA (too little work per phase); 384 threads (80 registers,

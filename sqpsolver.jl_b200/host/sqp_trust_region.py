@@ -84,6 +84,7 @@ class BatchSqpTR:
         self.rounds = 0
         self.timers = {"callbacks": 0.0, "device": 0.0}
         self.trace = None
+        self.trace_instances = None  # optional set of instance ids recorded in `trace` (None = all)
 
     # bounds may be per instance ([B,m]) or shared ([m])
     def _b(self, a, b):
@@ -191,11 +192,14 @@ class BatchSqpTR:
                     if self.trace is not None:
                         info = self.optimizer.last_info
                         for b in np.nonzero(mask)[0]:
+                            if self.trace_instances is not None and int(b) not in self.trace_instances:
+                                continue
                             self.trace.append({"b": int(b), "iter": int(self.iter[b]), "fr": bool(self.feasibility_restoration[b]),
                                                "x": self.x[b].copy(), "Delta": float(self.Delta[b]), "dE": self.dE[b].copy(),
                                                "h_val": self.h_val[b].copy(), "df": self.df[b].copy(), "E": self.E[b].copy(),
                                                "p": p[b].copy(), "lambda_qp": lam[b].copy(), "mult_x_U": mxU[b].copy(),
-                                               "mult_x_L": mxL[b].copy(), "status": int(st[b]), "info": info[b].copy()})
+                                               "mult_x_L": mxL[b].copy(), "status": int(st[b]), "info": info[b].copy(),
+                                               "lam": self.lam[b].copy()})
             self.timers["device"] += time.perf_counter() - t0
             self.p_lambda[act] = new_lam[act] - self.lam[act]
             self.p_mult_x_L[act] = new_L[act] - self.mult_x_L[act]

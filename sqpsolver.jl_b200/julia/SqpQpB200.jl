@@ -47,6 +47,7 @@ destroy_handle(h) = ccall((:sqpqp_destroy, libsqpqp), Cint, (Ptr{Cvoid},), h)
 mutable struct QpDevice
     h::Ptr{Cvoid}
     n::Int; m::Int; num_linear::Int; S::Int
+    slack_rows::Vector{Int}     # row (1-based) of every slack column, in the library's column order
     function QpDevice(n, m, num_linear, j_row::Vector{Int}, j_col::Vector{Int}, h_row::Vector{Int}, h_col::Vector{Int},
                       x_L, x_U, g_L, g_U; device = 0)
         h = create_handle(device)
@@ -56,7 +57,15 @@ mutable struct QpDevice
             h, 1, n, m, num_linear, length(j_row), j_row, j_col, length(h_row), h_row, h_col, x_L, x_U, g_L, g_U, 0))
         S = Ref{Int32}(0)
         check(h, ccall((:sqpqp_num_slacks, libsqpqp), Cint, (Ptr{Cvoid}, Ref{Int32}), h, S))
-        qp = new(h, n, m, num_linear, S[])
+        # slack columns of create_model! (subproblem_JuMP.jl:59-65): rows i > num_linear get u_i, and v_i as well when
+        # both bounds are finite -- the column order of sqpqp_num_slacks
+        slack_rows = Int[]
+        for i in (num_linear + 1):m
+            push!(slack_rows, i)
+            (g_L[i] > -Inf && g_U[i] < Inf) && push!(slack_rows, i)
+        end
+        @assert length(slack_rows) == S[]
+        qp = new(h, n, m, num_linear, S[], slack_rows)
         finalizer(q -> destroy_handle(q.h), qp)
         return qp
     end
@@ -73,8 +82,14 @@ function _solve(qp::QpDevice, phase::Integer, x_k::Vector{Float64}, Δ::Float64,
         (Ptr{Cvoid}, Int32, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
          Ptr{Float64}, Ptr{Float64}, Ref{Int32}, Ref{Info}),
         qp.h, phase, x_k, Δ, E_override, C_NULL, p, λ, mxL, mxU, slack, st, info))
-    # same 6-tuple as collect_solution! (subproblem_JuMP.jl:182, 514-563); p_slack left as a flat vector
-    return p, λ, mxU, mxL, slack[1:qp.S], MOI.TerminationStatusCode(Int(st[]))
+    # same 6-tuple as collect_solution! (subproblem_JuMP.jl:182, 514-563), p_slack in the reference's shape
+    # Dict{Int,Vector{Float64}} keyed by row (field type sqp.jl:22; filled at subproblem_JuMP.jl:519-529: one or two
+    # slack values per nonlinear row, absent for the linear rows)
+    p_slack = Dict{Int,Vector{Float64}}()
+    for (c, i) in enumerate(qp.slack_rows)
+        push!(get!(p_slack, i, Float64[]), slack[c])
+    end
+    return p, λ, mxU, mxL, p_slack, MOI.TerminationStatusCode(Int(st[]))
 end
 create_model!(qp::QpDevice, Δ) = nothing                                    # pattern was built in the constructor
 sub_optimize!(qp::QpDevice, x_k, Δ) = _solve(qp, 0, x_k, Δ)                  # subproblem_JuMP.jl:127-183

@@ -1,0 +1,189 @@
+"""GPU parity, whole trajectories: closed-loop replay of the device SQP runs against the CPU oracle on every BASELINE
+config (tests/support/closed_loop.py), the `lb > ub` box fallback on the device, and boundary B1 validated with the
+JuMP model the reference really builds (tests/support/jump_replay.py).
+
+Reference: sqp_trust_region.jl:98-223 (run!), subproblem_JuMP.jl:36-183, 352-393, 432-563, test/runtests.jl:12-14.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "support"))
+
+import closed_loop as cl  # noqa: E402
+from jump_replay import JumpReplay  # noqa: E402
+from oracle import qp_solver as qs  # noqa: E402
+from oracle.sqp_tr import Parameters as OParams, SqpTROracle  # noqa: E402
+from oracle.subproblem import trust_region_box  # noqa: E402
+from sqpsolver_jl_b200 import capi  # noqa: E402
+from sqpsolver_jl_b200.host.sqp_trust_region import BatchSqpTR, Parameters, SqpTR  # noqa: E402
+from sqpsolver_jl_b200.nlp.acopf import AcopfPolar  # noqa: E402
+from sqpsolver_jl_b200.nlp.networks import case9, synth_net  # noqa: E402
+from sqpsolver_jl_b200.nlp.toy import ReadmeToy, ToyExample  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+OK = cl.OK
+
+
+# ------------------------------------------------------------------------------------------------ closed loop
+@pytest.mark.parametrize("name,make,kw,every", [
+    ("toy", ToyExample, dict(max_iter=100), 1),
+    ("readme_toy", ReadmeToy, dict(max_iter=100), 1),
+    ("case9_mu1e4", lambda: AcopfPolar(case9()), dict(max_iter=100, init_mu=1e4), 1),
+    # the reference's own defaults (parameters.jl:17-29: init_mu = 1) as test/opf.jl:18-23 runs them
+    ("case9_default", lambda: AcopfPolar(case9()), dict(max_iter=100), 1),
+    ("case9_soc", lambda: AcopfPolar(case9()), dict(max_iter=100, init_mu=1e4, use_soc=True), 1),
+    # BASELINE configs[2]: case118-shaped network, trust-region variant, 100 SQP iterations, every subproblem checked
+    ("case118", lambda: AcopfPolar(synth_net(118, 186, 54, 118)), dict(max_iter=100, init_mu=1e5), 1),
+    ("case118_default", lambda: AcopfPolar(synth_net(118, 186, 54, 118)), dict(max_iter=40), 1),
+])
+def test_closed_loop_single_instance(built_lib, name, make, kw, every):
+    nlp = make()
+    dev = SqpTR(make(), Parameters(**kw))
+    trace = []
+    dev.run(trace=trace)
+    dev.close()
+    assert len(trace) >= 1
+    s = cl.check_trace(nlp, trace, oracle_every=every)
+    print(name, "status", dev.status, "iters", dev.iter, s)
+    assert s["worst_kkt"] <= 1e-6
+    assert s["marginal_mismatch"] <= max(2, s["n"] // 10), s   # marginal (violation < 1e-6) subproblems only, and few
+    assert s["oracle_solved"] >= 1
+    if name in ("toy", "readme_toy", "case9_mu1e4", "case9_soc"):
+        assert dev.status == 0
+
+
+def test_closed_loop_batch_case118(built_lib):
+    """BASELINE configs[4]: 1024 perturbed-load case118-shaped instances in one batch; 8 sampled instances are replayed
+    subproblem by subproblem against the oracle over the first 12 SQP rounds."""
+    B = 1024
+    net = synth_net(118, 186, 54, seed=118)
+    pd, qd = net.perturbed_loads(B)
+    nlp = AcopfPolar(net, pd=pd, qd=qd)
+    bt = BatchSqpTR(nlp, B, Parameters(max_iter=12, init_mu=1e5))
+    sample = [0, 17, 128, 341, 512, 682, 900, 1023]
+    bt.trace = []
+    bt.trace_instances = set(sample)
+    bt.run()
+    bt.close()
+    info_st = np.unique(bt.status, return_counts=True)
+    print("batch status", info_st)
+    for b in sample:
+        tr = [t for t in bt.trace if t["b"] == b]
+        assert len(tr) >= 10
+        one = AcopfPolar(net, pd=pd[b], qd=qd[b])
+        for t in tr:
+            t["b"] = None  # bounds of the single-instance NLP are 1-D
+        s = cl.check_trace(one, tr, oracle_every=1)
+        print("instance", b, s)
+        assert s["worst_kkt"] <= 1e-6 and s["marginal_mismatch"] <= 2
+
+
+def test_closed_loop_case2000(built_lib):
+    """BASELINE configs[3]: the ~2000-bus network, 10 SQP iterations; KKT on every subproblem, the oracle on three."""
+    make = lambda: AcopfPolar(synth_net(2000, 3000, 400, 2000))
+    nlp = make()
+    dev = SqpTR(make(), Parameters(max_iter=10, init_mu=1e5))
+    trace = []
+    dev.run(trace=trace)
+    dev.close()
+    assert len(trace) >= 10
+    s = cl.check_trace(nlp, trace, oracle_every=4)
+    print("case2000", dev.status, s)
+    assert s["worst_kkt"] <= 1e-6 and s["marginal_mismatch"] <= 1 and s["oracle_solved"] >= 2
+
+
+# ------------------------------------------------------------------------------------------------ box fallback
+def test_trust_region_box_fallback_on_device(engine):
+    """set_trust_region! with x_k OUTSIDE its bounds (subproblem_JuMP.jl:441-444): lb > ub -> lb = max(-D, min(0, v_lb)),
+    ub = min(D, max(0, v_ub)).  A separable strictly convex QP makes the box the only thing that decides p."""
+    n, m = 6, 1
+    idx = np.arange(1, n + 1)
+    x_L, x_U = np.full(n, -1.0), np.full(n, 1.0)
+    engine.setup_nlp(n, m, 1, np.ones(n, np.int64), idx, idx, idx, x_L, x_U, np.array([-1e3]), np.array([1e3]))
+    x_k = np.array([3.0, -4.0, 0.5, 1.0, -1.0, 10.0])   # 0, 1, 5 violate their bounds
+    delta = 0.5
+    df = np.array([-100.0, 100.0, -100.0, 100.0, -100.0, 100.0])
+    engine.update_nlp(np.ones(n), np.ones(n), df, np.zeros(m))
+    p, lam, mxL, mxU, _, st, info = engine.solve_tr(capi.PHASE_QP, x_k, delta)
+    assert st[0] in OK
+    lb, ub = trust_region_box(x_L - x_k, x_U - x_k, delta)
+    # x0: v = [-4,-2] -> lb=-0.5 > ub=-2 -> fallback [-0.5, 0];  x1: v = [3,5] -> fallback [0, 0.5];  x5: v=[-11,-9] -> [-0.5,0]
+    assert np.allclose(lb, [-0.5, 0.0, -0.5, -0.5, 0.0, -0.5]) and np.allclose(ub, [0.0, 0.5, 0.5, 0.0, 0.5, 0.0])
+    want = np.clip(-df, lb, ub)  # min 1/2 p'p + df'p over the box (row inactive)
+    assert np.abs(p[0] - want).max() <= 1e-7, (p[0], want)
+    assert (p[0] >= lb - 1e-9).all() and (p[0] <= ub + 1e-9).all()
+    res = qs.solve_qp(np.eye(n), df, np.ones((1, n)), np.array([-1e3]), np.array([1e3]), lb, ub)
+    assert np.abs(p[0] - res.x).max() <= 1e-6
+    assert np.abs((mxL[0] + mxU[0]) - res.col_dual).max() <= 1e-6 * max(1.0, np.abs(res.col_dual).max())
+
+
+# ------------------------------------------------------------------------------------------------ boundary B1
+@pytest.mark.parametrize("make,kw", [(ToyExample, dict(max_iter=100)), (ReadmeToy, dict(max_iter=100)),
+                                     (lambda: AcopfPolar(case9()), dict(max_iter=100, init_mu=1e4))])
+def test_generic_lane_with_the_jump_model_of_the_reference(built_lib, make, kw):
+    """A whole SQP solve through sqpqp_qp_setup / sqpqp_qp_solve with the model `create_model!` / `sub_optimize!` /
+    `sub_optimize_FR!` / `modify_constraints!` build (n + S columns, slacks fixed / freed through column bounds, paired
+    range rows at m + k, objective rebuilt per solve), flattened the way SqpQpB200.copy_to does and read back the way
+    collect_solution! does -- against the NLP lane (QpDevice) on the same problem."""
+    eng = capi.Engine(0)
+    try:
+        replay = []
+
+        def factory(data):
+            r = JumpReplay(data, eng)
+            replay.append(r)
+            return r
+
+        log_g, log_n = [], []
+        gen = SqpTROracle(make(), OParams(**kw), sub_factory=factory).run(log_g)
+        nlp_lane = SqpTR(make(), Parameters(**kw)).run(log_n)
+        nlp_lane.close()
+        assert gen.status == nlp_lane.status == 0
+        assert abs(gen.obj_val - nlp_lane.obj_val) <= 1e-6 * max(1.0, abs(nlp_lane.obj_val))
+        assert np.abs(gen.x - nlp_lane.x).max() <= 1e-5 * max(1.0, np.abs(nlp_lane.x).max())
+        # same trajectory, iteration by iteration: objective, trust region, step length, phase
+        assert len(log_g) == len(log_n), (len(log_g), len(log_n))
+        for a, b in zip(log_g, log_n):
+            assert a["fr"] == b["fr"] and a["accept"] == b["accept"]
+            for key in ("f", "Delta", "pinf", "inf_pr"):
+                assert abs(a[key] - b[key]) <= 1e-5 * max(1.0, abs(b[key])), (key, a["iter"], a[key], b[key])
+        r = replay[0]
+        assert r.n_solves == gen.n_qp
+        # the device structure is rebuilt only when the pattern of the model changes (QP <-> restoration LP objective)
+        assert r.n_setups <= 2 * sum(1 for a, b in zip(log_g, log_g[1:]) if a["fr"] != b["fr"]) + 2
+    finally:
+        eng.close()
+
+
+def test_jump_model_duals_land_on_the_right_rows(engine):
+    """One QP with every row kind (==, >=, <=, two-sided; linear and nonlinear) through the replayed JuMP model: the
+    multipliers mapped back by collect_solution! (:531-550) must equal the oracle's on the reference's row numbering."""
+    from oracle.subproblem import QpData, QpOracle
+    rng = np.random.default_rng(4)
+    n, m, ml = 7, 8, 3
+    A = rng.standard_normal((m, n))
+    xs = rng.uniform(-0.3, 0.3, n)
+    E = np.zeros(m)
+    Ax = A @ xs
+    c_lb = np.array([Ax[0], Ax[1] - 0.1, -np.inf, Ax[3], Ax[4] - 0.2, -np.inf, Ax[6] + 0.0, Ax[7] - 0.05])
+    c_ub = np.array([Ax[0], np.inf, Ax[2] + 0.1, Ax[3], np.inf, Ax[5] + 0.02, Ax[6] + 0.3, Ax[7] + 0.05])
+    M = rng.standard_normal((n, n))
+    Q = M @ M.T + np.eye(n)
+    c = 3.0 * rng.standard_normal(n)
+    import scipy.sparse as sp
+    data = QpData(sp.csr_matrix(Q), c, sp.csr_matrix(A), E, c_lb, c_ub, np.full(n, -0.5), np.full(n, 0.5), ml)
+    ora = QpOracle(data); ora.create_model(1.0)
+    xo, lo, uo, Lo, _, so = ora.sub_optimize(np.zeros(n), 1.0)
+    rep = JumpReplay(data, engine); rep.create_model(1.0)
+    xg, lg, ug, Lg, ps, sg = rep.sub_optimize(np.zeros(n), 1.0)
+    assert so in qs.OK_STATUSES and sg in qs.OK_STATUSES
+    assert rep.ncol == n + (m - ml) + 3          # u per nonlinear row, v for the == row and the two two-sided rows
+    assert len(rep.constr) == m + 2              # the `<=` halves of the two-sided rows appended at m + k
+    assert set(ps.keys()) == set(range(ml + 1, m + 1)) and all(v == 0.0 for vs in ps.values() for v in vs)
+    assert np.abs(xg - xo).max() <= 1e-6
+    assert np.abs(lg - lo).max() <= 1e-6 * max(1.0, np.abs(lo).max())
+    assert np.abs((ug + Lg) - (uo + Lo)).max() <= 1e-6 * max(1.0, np.abs(uo + Lo).max())
