@@ -57,7 +57,19 @@ struct Symbolic {
     int as_terms = 0;
     int64_t flops = 0;                   // of the sparse part (2 * pairs)
     bool ok = false;                     // false: a row of J is too long for the clique expansion
+    // kept for build_slot_programs(): per entry the P value index (-1: none), the range of its assembly terms, has_K
+    std::vector<int> as_h, as_ptr;
+    std::vector<char> hasK;
 };
+
+// The slot lists of the assembly and of the factorisation phases for ONE team shape: a task gets 2^lg lanes with
+// lg <= lgmax (the lanes of a task must sit in one warp: 32 lanes for a CTA team, 32 / G task lanes when G instances
+// are interleaved in a warp), and narrow phases are widened while one round of `team_lanes` lanes can hold them.
+struct SlotProg {
+    std::vector<int> ftask, fphase, aslot, aslot_d;
+    int ftasks = 0, atasks = 0;
+};
+inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, SlotProg& out);
 
 // J: m x ncols CSR (rb/re per row, so a prefix of each row can be used), P: symmetric-full CSR or null.
 // tail_max: largest dense tail (columns) the caller can hold; 0 disables the dense tail.
@@ -252,29 +264,15 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
             std::fill(cnt.begin(), cnt.end(), 0);
         }
     }
-    std::vector<char> hasK(S.nnzL, 0);
-    {
-        struct At { int e, q0, q1, h, d; };
-        std::vector<At> v;
-        for (int j = 0; j < n; ++j)
-            for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
-                const bool diag = e == S.Lp[j];
-                if (!diag && as_h[e] < 0 && as_ptr[e] == as_ptr[e + 1]) continue;  // pure fill: K_e = 0, nothing to assemble
-                hasK[e] = 1;
-                v.push_back(At{e, as_ptr[e], as_ptr[e + 1], as_h[e], diag ? S.perm[j] : -1});
-            }
-        std::stable_sort(v.begin(), v.end(), [](const At& a, const At& b) { return a.q1 - a.q0 > b.q1 - b.q0; });
-        S.atasks = (int)v.size();
-        for (const At& t : v) {
-            int lg = 0;
-            while (lg < 5 && (t.q1 - t.q0) > (4 << lg)) ++lg;
-            for (int lane = 0; lane < (1 << lg); ++lane) {
-                S.aslot.push_back(t.e | (lg << 26) | (lane == 0 ? (1 << 29) : 0));
-                S.aslot.push_back(t.q0 + lane); S.aslot.push_back(t.q1); S.aslot.push_back(t.h);
-                S.aslot_d.push_back(t.d);
-            }
+    S.as_h = as_h;
+    S.as_ptr = as_ptr;
+    S.hasK.assign(S.nnzL, 0);
+    for (int j = 0; j < n; ++j)
+        for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
+            const bool diag = e == S.Lp[j];
+            if (!diag && as_h[e] < 0 && as_ptr[e] == as_ptr[e + 1]) continue;  // pure fill: K_e = 0, nothing to assemble
+            S.hasK[e] = 1;
         }
-    }
     {
         int nslots = 0;
         for (int r = 0; r < m; ++r) nslots = std::max(nslots, Jre[r]);
@@ -283,59 +281,92 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
         for (int r = 0; r < m; ++r)
             for (int a = Jrb[r]; a < Jre[r]; ++a) S.jrow[a] = r;
     }
-    // ---- 4c. factorisation phases ----------------------------------------------------------------
+    // ---- 4c. slot lists of the assembly and the factorisation phases (CTA team: 32 lanes per task at most) ----------
     {
-        struct Tk { int tgt, q0, q1, aux; };
-        auto emit = [&](std::vector<Tk>& v, int kind) {
-            std::stable_sort(v.begin(), v.end(), [](const Tk& a, const Tk& b) { return a.q1 - a.q0 > b.q1 - b.q0; });
-            std::vector<int> lg(v.size(), 0);
-            long total = 0;
-            for (size_t t = 0; t < v.size(); ++t) {
-                int np = v[t].q1 - v[t].q0;
-                while (lg[t] < 5 && np > (8 << lg[t])) ++lg[t];
-                total += 1 << lg[t];
-            }
-            // narrow phase: spread every task over more lanes while one round of a 512-thread team can hold them
-            while (total * 2 <= 512) {
-                bool any = false;
-                total = 0;
-                for (size_t t = 0; t < v.size(); ++t) {
-                    if (lg[t] < 5) { ++lg[t]; any = true; }
-                    total += 1 << lg[t];
-                }
-                if (!any) break;
-            }
-            int s0 = (int)S.ftask.size() / 4, mp = 0;
-            for (size_t t = 0; t < v.size(); ++t) {
-                const Tk& k = v[t];
-                for (int lane = 0; lane < (1 << lg[t]); ++lane) {
-                    S.ftask.push_back(k.tgt | (lg[t] << 26) | (lane == 0 ? (1 << 29) : 0) | (hasK[k.tgt] ? (1 << 30) : 0));
-                    S.ftask.push_back(k.q0 + lane); S.ftask.push_back(k.q1); S.ftask.push_back(k.aux);
-                }
-                mp = std::max(mp, k.q1 - k.q0);
-            }
-            S.ftasks += (int)v.size();
-            S.fphase.push_back(s0); S.fphase.push_back((int)S.ftask.size() / 4); S.fphase.push_back(mp); S.fphase.push_back(kind);
-            v.clear();
-        };
-        std::vector<Tk> v;
-        for (int l = 0; l < S.nlev; ++l) {
-            for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j) v.push_back(Tk{S.Lp[j], S.fp_ptr[S.Lp[j]], S.fp_ptr[S.Lp[j] + 1], j});
-            emit(v, 0);
-            for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j)
-                for (int e = S.Lp[j] + 1; e < S.Lp[j + 1]; ++e) v.push_back(Tk{e, S.fp_ptr[e], S.fp_ptr[e + 1], j});
-            if (!v.empty()) emit(v, 1);
-        }
-        if (S.T > 0) {
-            // packed position (row-major lower triangle of the T x T tail) of every tail entry
-            for (int j = n0; j < n; ++j)
-                for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
-                    int r = S.Li[e] - n0, c = j - n0;
-                    v.push_back(Tk{e, S.fp_ptr[e], S.fp_ptr[e + 1], r * (r + 1) / 2 + c});
-                }
-            emit(v, 2);
-        }
+        SlotProg sp;
+        build_slot_programs(S, 5, 512, sp);
+        S.ftask.swap(sp.ftask); S.fphase.swap(sp.fphase); S.aslot.swap(sp.aslot); S.aslot_d.swap(sp.aslot_d);
+        S.ftasks = sp.ftasks; S.atasks = sp.atasks;
     }
     S.ok = true;
     return S;
+}
+
+inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, SlotProg& out) {
+    const int n = S.n, n0 = S.n0;
+    out = SlotProg();
+    // ---- assembly slots (4b) -------------------------------------------------------------------------------------
+    {
+        struct At { int e, q0, q1, h, d; };
+        std::vector<At> v;
+        for (int j = 0; j < n; ++j)
+            for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
+                if (!S.hasK[e]) continue;
+                v.push_back(At{e, S.as_ptr[e], S.as_ptr[e + 1], S.as_h[e], e == S.Lp[j] ? S.perm[j] : -1});
+            }
+        std::stable_sort(v.begin(), v.end(), [](const At& a, const At& b) { return a.q1 - a.q0 > b.q1 - b.q0; });
+        out.atasks = (int)v.size();
+        for (const At& t : v) {
+            int lg = 0;
+            while (lg < lgmax && (t.q1 - t.q0) > (4 << lg)) ++lg;
+            for (int lane = 0; lane < (1 << lg); ++lane) {
+                out.aslot.push_back(t.e | (lg << 26) | (lane == 0 ? (1 << 29) : 0));
+                out.aslot.push_back(t.q0 + lane); out.aslot.push_back(t.q1); out.aslot.push_back(t.h);
+                out.aslot_d.push_back(t.d);
+            }
+        }
+    }
+    // ---- factorisation phases (4c) ---------------------------------------------------------------------------------
+    struct Tk { int tgt, q0, q1, aux; };
+    auto emit = [&](std::vector<Tk>& v, int kind) {
+        std::stable_sort(v.begin(), v.end(), [](const Tk& a, const Tk& b) { return a.q1 - a.q0 > b.q1 - b.q0; });
+        std::vector<int> lg(v.size(), 0);
+        long total = 0;
+        for (size_t t = 0; t < v.size(); ++t) {
+            int np = v[t].q1 - v[t].q0;
+            while (lg[t] < lgmax && np > (8 << lg[t])) ++lg[t];
+            total += 1 << lg[t];
+        }
+        // narrow phase: spread every task over more lanes while one round of the team can hold them
+        while (total * 2 <= team_lanes) {
+            bool any = false;
+            total = 0;
+            for (size_t t = 0; t < v.size(); ++t) {
+                if (lg[t] < lgmax) { ++lg[t]; any = true; }
+                total += 1 << lg[t];
+            }
+            if (!any) break;
+        }
+        int s0 = (int)out.ftask.size() / 4, mp = 0, mlg = 0;
+        for (size_t t = 0; t < v.size(); ++t) {
+            const Tk& k = v[t];
+            for (int lane = 0; lane < (1 << lg[t]); ++lane) {
+                out.ftask.push_back(k.tgt | (lg[t] << 26) | (lane == 0 ? (1 << 29) : 0) | (S.hasK[k.tgt] ? (1 << 30) : 0));
+                out.ftask.push_back(k.q0 + lane); out.ftask.push_back(k.q1); out.ftask.push_back(k.aux);
+            }
+            mp = std::max(mp, k.q1 - k.q0);
+            mlg = std::max(mlg, lg[t]);
+        }
+        out.ftasks += (int)v.size();
+        // phase = (first slot, end slot, max pairs of a task | max lg << 24, kind)
+        out.fphase.push_back(s0); out.fphase.push_back((int)out.ftask.size() / 4); out.fphase.push_back(mp | (mlg << 24)); out.fphase.push_back(kind);
+        v.clear();
+    };
+    std::vector<Tk> v;
+    for (int l = 0; l < S.nlev; ++l) {
+        for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j) v.push_back(Tk{S.Lp[j], S.fp_ptr[S.Lp[j]], S.fp_ptr[S.Lp[j] + 1], j});
+        emit(v, 0);
+        for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j)
+            for (int e = S.Lp[j] + 1; e < S.Lp[j + 1]; ++e) v.push_back(Tk{e, S.fp_ptr[e], S.fp_ptr[e + 1], j});
+        if (!v.empty()) emit(v, 1);
+    }
+    if (S.T > 0) {
+        // packed position (row-major lower triangle of the T x T tail) of every tail entry
+        for (int j = n0; j < n; ++j)
+            for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
+                int r = S.Li[e] - n0, c = j - n0;
+                v.push_back(Tk{e, S.fp_ptr[e], S.fp_ptr[e + 1], r * (r + 1) / 2 + c});
+            }
+        emit(v, 2);
+    }
 }

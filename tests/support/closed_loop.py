@@ -134,9 +134,11 @@ def check_trace(nlp, trace, oracle_every=1, marginal=1e-6, qp_tol=1e-10, verbose
         tol = 1e-6 * max(1.0, abs(res.obj))
         same = np.abs(t["p"] - res.x).max() <= 1e-6 * max(1.0, np.abs(res.x).max())
         out["same_step"] += int(same)
-        convex = t["info"]["rho_box_floor"] <= 1e-8
+        # convex iff the Lagrangian Hessian handed to the QP is positive semidefinite (dense check; the 2000-bus
+        # network is too large for it and is treated as possibly nonconvex)
+        convex = P.shape[0] <= 1500 and np.linalg.eigvalsh(P.toarray()).min() >= -1e-9 * max(1.0, abs(P).max())
         if convex:
-            # no inertia correction was needed: K = P + Sigma was positive definite along the path -> compare values
+            # one optimal value: the device must reach it
             assert obj_d <= res.obj + tol + 2.0 * np.abs(q).sum() * 1e-9, ("objective worse than the oracle's", k, obj_d, res.obj)
         else:
             out["nonconvex"] += 1

@@ -57,7 +57,7 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
                     acc += L[ea] * L[eb];
                 }
             }
-            if (npairs != tk[2] - tk[1] || npairs > ph[2]) return -5;
+            if (npairs != tk[2] - tk[1] || npairs > (ph[2] & 0xffffff)) return -5;  // ph[2] = max pairs | max lg << 24
             double v = ((tk[0] >> 30) & 1 ? L[e] : 0.0) - acc;
             if (ph[3] == 0) {
                 if (!(v > 0.0)) return -2;
