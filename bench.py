@@ -219,11 +219,12 @@ def run_reference(args):
 
     net, batch, wname = make_workload(args)
     cores = os.cpu_count() or 1
-    pd, qd = net.perturbed_loads(cores)
+    ninst = min(batch, 2 * cores)   # bounded sample of the batch: two instances per core and step
+    pd, qd = net.perturbed_loads(ninst)
     kw = sqp_params(args)
-    # one "step" = one SQP iteration on each of `cores` instances in parallel (bounded sample of the batch)
+    # one "step" = one SQP iteration on each of `ninst` instances, `cores` at a time (bounded sample of the batch)
     with mp.Pool(cores) as pool:
-        jobs = lambda iters: [(net, pd[b], qd[b], kw, iters) for b in range(cores)]
+        jobs = lambda iters: [(net, pd[b], qd[b], kw, iters) for b in range(ninst)]
         if args.warmup:
             pool.map(_oracle_sqp_worker, jobs(min(args.warmup, 2)))
         t0 = time.perf_counter()
@@ -235,10 +236,15 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wname, "sqp": kw, "sample": f"{cores} instances x {args.steps} SQP iterations"},
+        "config": {"workload": wname, "network": {"nbus": net.nbus, "nbranch": net.nbranch, "ngen": net.ngen, "seed": net.meta.get("seed")},
+                   "batch_total": batch, "sqp": kw,
+                   "step": "one SQP iteration (evaluation + QP subproblem solve) on each sampled instance",
+                   "sample": f"{ninst} of the {batch} instances x {args.steps} SQP iterations", "extrapolated": ninst < batch,
+                   "sharding": "one process per host core"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cores} instances of the batch in parallel processes, {args.steps} SQP iterations each; "
-                                   "CPU restatement (SciPy/SuperLU interior point), not Ipopt"},
+                         "sample": f"{ninst} instances of the batch over {cores} processes, {args.steps} SQP iterations each (the rate "
+                                   "of the full batch is the same: instances are independent); CPU restatement (SciPy/SuperLU "
+                                   "interior point), not Ipopt"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "qp_solves": int(sum(o[1] for o in out)),
     }
@@ -262,6 +268,11 @@ def main():
     ap.add_argument("--no-spmv", action="store_true", help="skip the 2000-bus SpMV roofline leg")
     ap.add_argument("--no-device-eval", action="store_true", help="skip the full solve with the device-side evaluator")
     ap.add_argument("--spmv-batch", type=int, default=2048)
+    ap.add_argument("--layout-G", dest="layout_G", type=int, default=0, help="instances interleaved per CTA (0 auto, 1 off, 2/4/8)")
+    ap.add_argument("--layout-threads", dest="layout_threads", type=int, default=0)
+    ap.add_argument("--layout-ctas", dest="layout_ctas", type=int, default=0)
+    ap.add_argument("--layout-tail", dest="layout_tail", type=int, default=-1)
+    ap.add_argument("--no-single2000", action="store_true", help="skip the single-instance 2000-bus leg (BASELINE configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -300,12 +311,16 @@ def main():
     # ---- untimed set-up: run the real batched SQP on the device, record the first rounds ----
     rec = []
 
-    sqp = BatchSqpTR(nlp, Bl, Parameters(**kw), device=local)
+    layout = dict(G=args.layout_G, threads=args.layout_threads, ctas_per_sm=args.layout_ctas, tail=args.layout_tail)
+    sqp = BatchSqpTR(nlp, Bl, Parameters(**kw), device=local, layout=layout)
+    # replayed rounds are sampled UNIFORMLY over the whole solve (round 1, 1 + T/R, ...): late rounds carry the stragglers
+    stride = max(1, args.sqp_max_iter // max(1, args.rounds))
+    sample_rounds = {1 + k * stride for k in range(args.rounds)}
     # record at the moment of each QP call: hook the stats counter via the merit call order
     orig_solve = sqp.optimizer._solve
 
     def solve_hook(phase, x_k, delta, E_override=None, active=None):
-        if phase in (capi.PHASE_QP, capi.PHASE_FR) and len(rec) < args.rounds:
+        if phase in (capi.PHASE_QP, capi.PHASE_FR) and sqp.rounds in sample_rounds:
             act = np.ones(Bl, bool) if active is None else np.asarray(active, bool)
             if rec and rec[-1].get("round") == sqp.rounds:
                 rec[-1]["fr" if phase == capi.PHASE_FR else "qp"] = act.astype(np.int32)
@@ -327,6 +342,10 @@ def main():
             "qp_solves": int(sqp.n_qp.sum()), "status_counts": {int(k): int(v) for k, v in zip(*np.unique(sqp.status, return_counts=True))},
             "device_s": sqp.timers["device"], "callbacks_s": sqp.timers["callbacks"],
             "solve_kernel_s": sqp.optimizer.stats["solve_ms"] / 1e3}
+    full["qp_solves_per_sec_wall"] = full["qp_solves"] / t_sqp                      # host NLP callbacks + PCIe + kernels
+    full["qp_solves_per_sec_kernel"] = full["qp_solves"] / max(full["solve_kernel_s"], 1e-9)
+    full["ms_per_round_kernel"] = 1e3 * full["solve_kernel_s"] / max(1, full["rounds"])
+    full["converged_instances"] = int((sqp.status == 0).sum())
     res_local = pack_results(sqp.status, sqp.iter, sqp.obj_val)
     res_all = gather_results(res_local, batch, device=dev)  # the one collective of the path (NCCL, 16 B/instance)
     eng = sqp.optimizer.engine
@@ -443,6 +462,17 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = float(np.mean(ach)) if ach else 0.0
+        kernel_name = eng.last_solve_kernel
+        # dram__bytes of ONE launch of the dominant kernel from an `ncu --set full` capture of THIS bench command,
+        # written next to the profile summary by tools/ncu_traffic.py (kernel name, launch shape and git revision inside);
+        # reported only when it was taken for the kernel this run launched, else null
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if tr.get("kernel") == kernel_name and tr.get("batch_per_gpu") == Bl and tr.get("workload") == args.workload:
+                traffic = tr
+        except (OSError, ValueError):
+            pass
         b_it, b_f = bytes_model_ipm(n, m, nnzJ, nnzH, max(chol["nnzL"], 1))
         h2d = int(sum(rec[0][k].nbytes for k in ("dE", "h_val", "df", "E", "x", "Delta", "qp")) + rec[0]["x"].nbytes * 2
                   + rec[0]["E"].nbytes * 2 + rec[0]["lam"].nbytes + 2 * rec[0]["mxU"].nbytes)
@@ -463,13 +493,10 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on this workload (first QP
-                         # round, 1024 instances) from the ncu --set full capture summarised in profiles/r01_ncu_summary_v2.md
-                         # section 6 (final build, k_solve_cta<384,2,1>); a recorded measurement, not re-measured by this run (null when the shard differs)
-                         "traffic": 36.1e9 if (Bl == 1024 and args.workload == "batch118") else None,
-                         "traffic_algorithmic_bytes_same_launch": 25.0e9 if (Bl == 1024 and args.workload == "batch118") else None,
-                         # launch shape chosen by launch_solve (csrc/sqpqp.cu): two 384-thread CTAs per SM from 2 x 148 instances up
-                         "kernel": "k_solve_cta<384,2,1>" if Bl >= 296 else "k_solve_cta<512,1,1>",
+                         "traffic": traffic["dram_bytes"] if traffic else None,
+                         "traffic_source": ({k: traffic[k] for k in ("profile", "launch", "algorithmic_bytes_same_launch", "git") if k in traffic}
+                                            if traffic else None),
+                         "kernel": kernel_name,  # from the library (sqpqp_last_solve_kernel): the launch rule lives there
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "note": "achieved = algorithmic bytes / CUDA-event duration of the solve kernel; bytes = per-instance fp64 values each "
                                  "phase of an interior-point iteration must touch once (%d B per iteration + %d B per Cholesky factorisation, "
@@ -479,6 +506,11 @@ def main():
             "solver": {"method": "interior point + batched sparse Cholesky (ADMM/PCG fallback)", "ipm_iters_mean": ipm_it,
                        "ipm_iters_max": ipm_max, "admm_fallbacks": fallbacks, "chol": chol},
             "full_sqp_solve": full,
+            "note": ("value/e2e time the hot path (scatter + batched QP solve) on %d SQP rounds sampled uniformly over the solve; the NLP "
+                     "callbacks are outside them.  The whole batched SQP solve incl. callbacks runs at full_sqp_solve.qp_solves_per_sec_wall. "
+                     "%d of %d instances end with status 0: on this workload the reference algorithm as coded (Hessian multiplier sign, "
+                     "sqp.jl:93) stalls at the iteration limit on BOTH sides (oracle and device, DESIGN.md section 8)"
+                     % (R, full["converged_instances"], Bl)),
             "results_gathered": {"instances": int(res_all.shape[0]), "status_counts": {int(k): int(v) for k, v in zip(*np.unique(res_all["status"], return_counts=True))}},
         }
         if not args.no_spmv and world == 1:
@@ -497,21 +529,43 @@ def main():
                 "max_rel_objective_diff_vs_host_evaluator": float(np.max(np.abs(sqp2.obj_val - sqp.obj_val) / np.maximum(1.0, np.abs(sqp.obj_val))))}
             sqp2.close()
         if not args.no_cpu_baseline and world == 1:
-            tcb0 = time.perf_counter()
-            times = []
+            # 1 thread and nproc threads, median of >= 5 repetitions after one warm-up, per QP solve
+            import multiprocessing as mp
+            jobs = []
             k = 0
-            while k < args.cpu_sample and time.perf_counter() - tcb0 < 40.0:
+            while len(jobs) < max(6, args.cpu_sample + 1) and k < 64 * R:
                 r = rec[k % R]
                 b = (k // R) % Bl
                 if r["qp"][b]:
-                    dt, st = _oracle_qp_worker((net, pd[b], qd[b], {"dE": r["dE"][b], "h_val": r["h_val"][b], "df": r["df"][b],
-                                                                     "E": r["E"][b], "x": r["x"][b], "Delta": float(r["Delta"][b])}))
-                    times.append(dt)
+                    jobs.append((net, pd[b], qd[b], {"dE": r["dE"][b], "h_val": r["h_val"][b], "df": r["df"][b],
+                                                     "E": r["E"][b], "x": r["x"][b], "Delta": float(r["Delta"][b])}))
                 k += 1
+            tcb0 = time.perf_counter()
+            times = []
+            for i, jb in enumerate(jobs):
+                dt, st = _oracle_qp_worker(jb)
+                if i > 0:  # the first solve is the warm-up
+                    times.append(dt)
+                if time.perf_counter() - tcb0 > 25.0 and len(times) >= 5:
+                    break
+            cores = os.cpu_count() or 1
+            par = None
+            try:
+                with mp.Pool(cores) as pool:
+                    pool.map(_oracle_qp_worker, [jobs[i % len(jobs)] for i in range(cores)])  # warm-up (imports, caches)
+                    tp0 = time.perf_counter()
+                    outp = pool.map(_oracle_qp_worker, [jobs[i % len(jobs)] for i in range(2 * cores)])
+                    par = 2 * cores / (time.perf_counter() - tp0)
+            except OSError:
+                pass
             if times:
-                line["cpu_baseline"] = {"value": len(times) / float(np.sum(times)), "unit": UNIT, "cores": 1, "kind": "port",
-                                        "sample": f"{len(times)} of the replayed QP subproblems (instances 0.. of rounds 1..{R}) solved one "
-                                                  "after another by the CPU oracle (SciPy/SuperLU interior point, not Ipopt)"}
+                line["cpu_baseline"] = {"value": 1.0 / float(np.median(times)), "unit": UNIT, "cores": 1, "kind": "port",
+                                        "value_all_cores": par, "all_cores": cores,
+                                        "median_s_per_qp": float(np.median(times)), "repetitions": len(times),
+                                        "sample": f"{len(times)} of the replayed QP subproblems (rounds sampled over the solve) solved one after "
+                                                  "another by the CPU oracle after one warm-up solve: 1 / median time; value_all_cores = "
+                                                  f"{2 * cores} of them over a pool of {cores} processes.  CPU restatement (SciPy/SuperLU "
+                                                  "interior point), not Ipopt"}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)

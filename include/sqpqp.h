@@ -261,6 +261,9 @@ int64_t sqpqp_launch_count(sqpqp_handle h);
 /* Device time (ms) of the last sqpqp_solve_tr's solve kernel, from CUDA events on
  * the handle's stream. */
 double sqpqp_last_solve_ms(sqpqp_handle h);
+/* Name and launch shape of the interior-point kernel the last solve launched (e.g. "k_solve_cta<384,2,1>",
+ * "k_solve_ilv<4,512,1>", "k_solve_grid"): the launch rule lives in the library, reports read it from here. */
+const char* sqpqp_last_solve_kernel(sqpqp_handle h);
 
 #ifdef __cplusplus
 }

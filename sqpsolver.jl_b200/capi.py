@@ -81,7 +81,7 @@ EXPORTS = [
     "sqpqp_create", "sqpqp_destroy", "sqpqp_last_error", "sqpqp_default_options", "sqpqp_set_options", "sqpqp_stream",
     "sqpqp_setup_nlp", "sqpqp_update_nlp", "sqpqp_update_nlp_device", "sqpqp_solve_tr", "sqpqp_num_slacks",
     "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
-    "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
+    "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_last_solve_kernel", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
     "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read", "sqpqp_debug_set", "sqpqp_linesearch_terms", "sqpqp_acopf_setup", "sqpqp_acopf_eval_update",
 ]
 
@@ -158,6 +158,8 @@ def lib():
     L.sqpqp_launch_count.restype = C.c_int64
     L.sqpqp_last_solve_ms.argtypes = [vp]
     L.sqpqp_last_solve_ms.restype = C.c_double
+    L.sqpqp_last_solve_kernel.argtypes = [vp]
+    L.sqpqp_last_solve_kernel.restype = C.c_char_p
     for name in EXPORTS:
         f = getattr(L, name)
         if f.restype is C.c_int:  # default restype
@@ -229,6 +231,13 @@ class Engine:
                 raise KeyError(k)
             setattr(self.opts, k, v)
         self._ck(self.L.sqpqp_set_options(self.h, C.byref(self.opts)))
+
+    def set_layout(self, G=0, threads=0, ctas_per_sm=0, tail=-1):
+        """Layout of the batched interior-point launch, effective at the next setup_nlp: G instances interleaved per CTA
+        (0 = auto, 1 = one CTA per instance, 2 / 4 / 8), its CTA size (0 = auto, 256 / 512 / 1024), CTAs per SM
+        (0 = auto) and the cap of the dense tail of the factor in columns (-1 = auto).  Tuning / A-B runs."""
+        for what, v in ((2, G), (3, threads), (4, ctas_per_sm), (1, tail)):
+            self._ck(self.L.sqpqp_debug_set(self.h, what, int(v)))
 
     # ---- NLP lane --------------------------------------------------------------
     def setup_nlp(self, n, m, m_lin, j_row, j_col, h_row, h_col, x_L, x_U, g_L, g_U, batch=1):
@@ -443,6 +452,10 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.L.sqpqp_launch_count(self.h))
+
+    @property
+    def last_solve_kernel(self):
+        return self.L.sqpqp_last_solve_kernel(self.h).decode()
 
     @property
     def last_solve_ms(self):

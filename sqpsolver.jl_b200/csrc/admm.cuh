@@ -769,13 +769,15 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
     double* os = P.o_slack + (size_t)inst * (P.S > 0 ? P.S : 1);
     for_n(T, n, [&](int j) {
         double pv = 0.0, rcost = 0.0;
-        if (okst) { pv = D[j] * x[j]; rcost = -yb[j] / (D[j] * c); }
+        // a fixed column (lb == ub: trust-region box collapsed onto a bound, or a slack column fixed by the generic lane)
+        // returns its bound exactly, as a solver that eliminates fixed variables does
+        if (okst) { pv = D[j] * ((xl[j] == xu[j]) ? xl[j] : x[j]); rcost = -yb[j] / (D[j] * c); }
         op[j] = pv;
         oL[j] = rcost > 0.0 ? rcost : 0.0;
         oU[j] = rcost < 0.0 ? rcost : 0.0;
     });
     for_n(T, m, [&](int i) { ol[i] = okst ? -(Es[i] * yc[i]) / c : 0.0; });
-    for_n(T, P.S, [&](int s) { os[s] = (okst && phase == SQPQP_PHASE_FR) ? D[n + s] * x[n + s] : 0.0; });
+    for_n(T, P.S, [&](int s) { os[s] = (okst && phase == SQPQP_PHASE_FR) ? D[n + s] * ((xl[n + s] == xu[n + s]) ? xl[n + s] : x[n + s]) : 0.0; });
     // warm start for the next solve of this instance (unscaled)
     if (okst && phase != SQPQP_PHASE_LP && phase != SQPQP_PHASE_FR) {
         for_n(T, n, [&](int j) { xw[j] = D[j] * x[j]; ybw[j] = yb[j] / (D[j] * c); });

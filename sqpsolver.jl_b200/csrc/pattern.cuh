@@ -149,6 +149,8 @@ struct ScatterJob {
     const double* vals;     // [batch][nsrc]
     const double* consts;   // shared
     double* out;            // [batch][nslots]
+    double* out_ilv;        // nullable: the same values group-interleaved, [batch / G][nslots][G] (ilv.cuh)
+    int G;
 };
 __global__ void k_scatter(ScatterJob a, ScatterJob b, ScatterJob c, int batch) {
     const ScatterJob* jobs[3] = {&a, &b, &c};
@@ -165,6 +167,7 @@ __global__ void k_scatter(ScatterJob a, ScatterJob b, ScatterJob c, int batch) {
                 acc += (src < J.nsrc) ? v[src] : J.consts[src - J.nsrc];
             }
             J.out[(int64_t)inst * J.nslots + s] = acc;
+            if (J.out_ilv) J.out_ilv[((int64_t)(inst / J.G) * J.nslots + s) * J.G + (inst % J.G)] = acc;
         }
     }
 }

@@ -17,6 +17,7 @@
 #include "pattern.cuh"
 #include "admm.cuh"
 #include "ipm.cuh"
+#include "ilv.cuh"
 #include "merit.cuh"
 #include "spmv.cuh"
 #include "acopf.cuh"
@@ -67,6 +68,14 @@ struct sqpqp_handle_s {
     int spmv_ctas_per_sm = 8;
     AcopfDev acopf{};       // device-side ACOPF evaluator (acopf.cuh); nb == 0: not set up
     double* d_f = nullptr;  // [batch] objective values of the evaluator  // CSR-stream row blocks of J (normal phase), J' and H
+    // interleaved batch path (ilv.cuh): G instances per CTA.  ilv_G: 0 = auto, 1 = off, 2 / 4 / 8; chosen at setup
+    int ilv_G = 0, ilv_threads = 0, ilv_occ = 0;
+    int G = 1;                       // in effect for the current problem
+    IlvDev ilv{}, ilv_fr{};
+    bool has_ilv = false, has_ilv_fr = false;
+    size_t ilv_dyn = 0, ilv_fr_dyn = 0;
+    int ilv_nt = 512, ilv_minb = 1;
+    std::string last_kernel;         // name of the interior-point kernel of the last solve launch (sqpqp_last_solve_kernel)
     // generic-lane bookkeeping
     bool generic = false;
 };
@@ -385,6 +394,8 @@ extern "C" double sqpqp_last_solve_ms(sqpqp_handle h) {
     return h->last_ms;
 }
 
+extern "C" const char* sqpqp_last_solve_kernel(sqpqp_handle h) { return h ? h->last_kernel.c_str() : ""; }
+
 extern "C" int sqpqp_set_options(sqpqp_handle h, const sqpqp_options* o) {
     if (!h || !o) return SQPQP_E_BADARG;
     if (o->threads < 0 || o->threads > 512 || (o->threads % 32) != 0) return fail(h, SQPQP_E_BADARG, "threads must be a multiple of 32 in [0,512]");
@@ -444,6 +455,9 @@ extern "C" int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value) {  /
     if (!h) return SQPQP_E_BADARG;
     if (what == 0 && value > 0) h->spmv_ctas_per_sm = value;
     if (what == 1) h->tail_override = value;
+    if (what == 2 && (value == 0 || value == 1 || value == 2 || value == 4 || value == 8)) h->ilv_G = value;
+    if (what == 3 && (value == 0 || value == 256 || value == 512 || value == 1024)) h->ilv_threads = value;
+    if (what == 4 && value >= 0 && value <= 2) h->ilv_occ = value;
     return 0;
 }
 
@@ -460,6 +474,35 @@ extern "C" int sqpqp_num_slacks(sqpqp_handle h, int32_t* S) {
     if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
     *S = h->P.S;
     return 0;
+}
+
+// instances interleaved per CTA for a batch of this size when the caller did not choose (sqpqp_debug_set what = 2)
+// Measured on BASELINE configs[4] (profiles/r02_layout_ab.md): the interleaved layout is never faster than one CTA per
+// instance on the case118-shaped batch -- the G instances of a group iterate in lock step, so a group runs for the
+// iteration count of its slowest member (mean 28, max 46-74 per round) -- hence auto = off.
+static int ilv_auto_G(sqpqp_handle h, int batch) {
+    (void)h; (void)batch;
+    return 1;
+}
+
+template <int G, int NT, int MINB>
+static cudaError_t launch_ilv_t(sqpqp_handle h, const DevOpts& O, int phase, const IlvDev& X, size_t dyn) {
+    cudaError_t e = cudaFuncSetAttribute(k_solve_ilv<G, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    int grid = X.ngroups < 65535 ? X.ngroups : 65535;
+    k_solve_ilv<G, NT, MINB><<<grid, NT, dyn, h->stream>>>(h->P, O, phase, X);
+    return cudaGetLastError();
+}
+static cudaError_t launch_ilv(sqpqp_handle h, const DevOpts& O, int phase, const IlvDev& X, size_t dyn) {
+    const int G = h->G, NT = h->ilv_nt, MB = h->ilv_minb;
+    // the shapes kept after the A/B of profiles/r02_layout_ab.md (the layout is off by default: it lost on the headline
+    // workload); other (threads, CTAs per SM) requests fall back to the nearest one
+    (void)NT;
+    if (G == 2) return launch_ilv_t<2, 512, 2>(h, O, phase, X, dyn);
+    if (G == 4 && MB == 2) return launch_ilv_t<4, 512, 2>(h, O, phase, X, dyn);
+    if (G == 4) return launch_ilv_t<4, 512, 1>(h, O, phase, X, dyn);
+    if (G == 8) return launch_ilv_t<8, 512, 1>(h, O, phase, X, dyn);
+    return cudaErrorInvalidConfiguration;
 }
 
 // ---- setup -------------------------------------------------------------------------------
@@ -568,12 +611,24 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
     P.lgT = lg_lanes((double)pt.nslots / P.Ne);
     P.lgH = lg_lanes(n ? (double)ph.nslots / n : 1.0);
 
-    // per-instance storage
-    const size_t B = batch;
+    // ---- layout of the batched interior-point path: G instances interleaved per CTA (ilv.cuh), or one CTA per instance ----
+    // auto: from four instances per SM up, groups of 4 (full 32-byte sectors per gather, 2 groups resident per SM do not
+    // fit its shared memory, so fewer instances than that are better served by the one-CTA-per-instance team)
+    int G = h->ilv_G;
+    if (G == 0) G = ilv_auto_G(h, batch);
+    if (batch < 2 || m == 0) G = 1;
+    h->G = G;
+    h->has_ilv = h->has_ilv_fr = false;
+    h->ilv_nt = 512;
+    h->ilv_minb = (G == 2) ? 2 : (G == 4 && h->ilv_occ == 2 ? 2 : 1);
+    // per-instance storage (workspace arrays padded to whole groups)
+    const size_t B = (G > 1) ? ((size_t)batch + G - 1) / G * G : (size_t)batch;
     DALLOC(P.Jv, B * P.nnzJ); DALLOC(P.Tv, B * P.nnzT); DALLOC(P.Hv, B * P.nnzH);
     DALLOC(P.Jsv, B * P.nnzJ); DALLOC(P.Tsv, B * P.nnzT); DALLOC(P.Hsv, B * P.nnzH);
     for (int k = 0; k < N_COUNT; ++k) DALLOC(P.nv[k], B * P.Ne);
     for (int k = 0; k < M_COUNT; ++k) DALLOC(P.mv[k], B * (m > 0 ? m : 1));
+    double *Jvi = nullptr, *Tvi = nullptr, *Hvi = nullptr;
+    if (G > 1) { DALLOC(Jvi, B * P.nnzJ); DALLOC(Tvi, B * P.nnzT); DALLOC(Hvi, B * P.nnzH); }
     DALLOC(P.codeC, B * (m > 0 ? m : 1)); DALLOC(P.prevC, B * (m > 0 ? m : 1)); DALLOC(P.triedC, B * (m > 0 ? m : 1));
     DALLOC(P.codeB, B * P.Ne); DALLOC(P.prevB, B * P.Ne); DALLOC(P.triedB, B * P.Ne);
     DALLOC(P.rho_w, B);
@@ -644,8 +699,26 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         // shared memory one CTA gets when four CTAs share an SM, next to the inverse diagonal and the
         // solve scratch when those fit as well.  A single large instance runs on the cooperative grid
         // (no CTA-local shared memory across the team) and keeps the plain level-scheduled code.
+        // shared-memory budget of one interleaved CTA: the opt-in maximum (one CTA per SM) or half an SM, minus its
+        // static reduction scratch
+        const size_t ilv_static = (size_t)2 * ILV_KMAX * (h->ilv_nt / 32) * G * sizeof(double);
+        int per_sm_smem = 0, optin_smem = 0;
+        cudaDeviceGetAttribute(&per_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device);
+        cudaDeviceGetAttribute(&optin_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+        const size_t ilv_budget = (h->ilv_minb >= 2 ? (size_t)per_sm_smem / 2 - 1024 : (size_t)optin_smem) - ilv_static - 256;
+        auto ilv_yw_resident = [&](int ncols) -> bool {  // solve scratch next to a tail of at least 48 columns?
+            return (size_t)ncols * G * sizeof(double) + (size_t)52 * 53 / 2 * G * sizeof(double) <= ilv_budget;
+        };
         auto tail_cap = [&](int ncols) -> int {
             if (batch == 1 && (size_t)P.Ne + m > 6000) return 0;
+            if (G > 1) {
+                size_t cap = ilv_budget / sizeof(double) / G;  // doubles per instance
+                if (ilv_yw_resident(ncols)) cap -= ncols;
+                int lim = h->tail_override >= 0 ? h->tail_override : 96;
+                int t = 0;
+                while (t < lim && (size_t)(t + 4) * (t + 5) / 2 <= cap) ++t;
+                return t;
+            }
             if (h->tail_override >= 0) return h->tail_override;  // sqpqp_debug_set(h, 1, columns): tuning runs only
             size_t cap = (size_t)h->cta2_smem / sizeof(double);
             size_t vec = 2 * (size_t)((ncols + 1) & ~1);
@@ -655,6 +728,33 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             // sparse levels it replaces (measured on the case118-shaped batch: T = 48 / 92 / 128 -> 79 / 61 / 67 ms)
             while (t < 96 && (size_t)(t + 4) * (t + 5) / 2 + (size_t)((t + 2) & ~1) <= cap) ++t;
             return t;
+        };
+        // slot lists for 32 / G lanes per task + shared-memory placement of the interleaved path
+        auto build_ilv = [&](const Symbolic& Sy, const CholDev& base, int ncols, IlvDev* X, size_t* dyn) -> int {
+            int lgG = 0;
+            while ((1 << lgG) < G) ++lgG;
+            SlotProg sp;
+            build_slot_programs(Sy, 5 - lgG, h->ilv_nt / G, sp);
+            X->C = base;
+            X->C.nphase = (int)sp.fphase.size() / 4;
+            X->C.n_aslot = (int)sp.aslot_d.size();
+            for (int k = 0; k < 4; ++k) sp.fphase.push_back(0);
+            if (sp.ftask.empty()) sp.ftask.assign(4, 0);
+            if (sp.aslot.empty()) { sp.aslot.assign(4, 0); sp.aslot_d.assign(1, -1); }
+            int rc3;
+            if ((rc3 = up(sp.ftask, (const int**)&X->C.ftask)) || (rc3 = up(sp.fphase, (const int**)&X->C.fphase)) ||
+                (rc3 = up(sp.aslot, (const int**)&X->C.aslot)) || (rc3 = up(sp.aslot_d, &X->C.aslot_d)))
+                return rc3;
+            X->Jvi = Jvi; X->Tvi = Tvi; X->Hvi = Hvi;
+            X->ngroups = (int)(B / G);
+            const size_t Tp = ((size_t)Sy.T + 3) & ~(size_t)3;
+            size_t off = 0;
+            X->off_D = -1; X->off_yw = -1; X->off_dinv = -1;
+            if (Sy.T > 0) { X->off_D = 0; off = Tp * (Tp + 1) / 2 * G; }
+            if ((off + (size_t)ncols * G) * sizeof(double) <= ilv_budget) { X->off_yw = (int)off; off += (size_t)ncols * G; }
+            *dyn = off * sizeof(double);
+            if (*dyn > ilv_budget) return fail(h, SQPQP_E_STATE, "dense tail of the factor does not fit the shared memory of the interleaved launch");
+            return 0;
         };
         CUDA_OK(cudaStreamSynchronize(h->stream));
         {   // CSR-stream SpMV plans (spmv.cuh): row blocks of <= SPMV_CHUNK value slots, shared by the batch
@@ -683,6 +783,11 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             P.has_chol = 1;
             h->chol_nnzL = Sy.nnzL; h->chol_nlev = Sy.nlev; h->chol_flops = Sy.flops; h->chol_tail = Sy.T;
             h->chol_nlev_total = Sy.nlev_total;
+            if (G > 1) {
+                rc2 = build_ilv(Sy, P.chol, n, &h->ilv, &h->ilv_dyn);
+                if (rc2) return rc2;
+                h->has_ilv = true;
+            }
         }
         // feasibility-restoration LP: columns [J | S], no quadratic term
         P.has_chol_fr = 0;
@@ -695,6 +800,11 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
                 DALLOC(P.yw_fr, B * (size_t)P.Ne);
                 DALLOC(P.dinv_fr, B * (size_t)P.Ne);
                 P.has_chol_fr = 1;
+                if (G > 1) {
+                    rc2 = build_ilv(Sf, P.chol_fr, P.Ne, &h->ilv_fr, &h->ilv_fr_dyn);
+                    if (rc2) return rc2;
+                    h->has_ilv_fr = true;
+                }
             }
         }
     }
@@ -709,9 +819,9 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
     DALLOC(P.gred, (size_t)2 * SQPQP_MAX_RED * P.gred_stride);
 
     // scatter jobs
-    h->jobJ = ScatterJob{P.nnzJ, (int)nnz_j, pj.seg_ptr, pj.seg_src, h->d_dE, d_ssign, P.Jv};
-    h->jobT = ScatterJob{P.nnzT, (int)nnz_j, pt.seg_ptr, pt.seg_src, h->d_dE, d_ssign, P.Tv};
-    h->jobH = ScatterJob{P.nnzH, (int)nnz_h, ph.seg_ptr, ph.seg_src, h->d_hval, nullptr, P.Hv};
+    h->jobJ = ScatterJob{P.nnzJ, (int)nnz_j, pj.seg_ptr, pj.seg_src, h->d_dE, d_ssign, P.Jv, Jvi, G};
+    h->jobT = ScatterJob{P.nnzT, (int)nnz_j, pt.seg_ptr, pt.seg_src, h->d_dE, d_ssign, P.Tv, Tvi, G};
+    h->jobH = ScatterJob{P.nnzH, (int)nnz_h, ph.seg_ptr, ph.seg_src, h->d_hval, nullptr, P.Hv, Hvi, G};
     CUDA_OK(cudaStreamSynchronize(h->stream));
     CUDA_OK(cudaGetLastError());
     h->setup_done = true;
@@ -914,6 +1024,7 @@ static int launch_solve(sqpqp_handle h, int phase) {
     if (team == 2) {
         void* args[] = {(void*)&P, (void*)&O, (void*)&phase};
         CUDA_OK(cudaLaunchCooperativeKernel((void*)k_solve_grid, dim3(h->coop_blocks), dim3(256), args, 0, h->stream));
+        h->last_kernel = "k_solve_grid";
     } else {
         int threads = pick_threads(h, phase);
         int grid = (int)(B < 65535 ? B : 65535);
@@ -970,7 +1081,15 @@ static int launch_solve(sqpqp_handle h, int phase) {
         };
         if (threads > 512) threads = 512;
         if (cfg == 4 && threads > 256) threads = 256;
-        if (ipm) launch(1);
+        const bool use_ilv = ipm && h->G > 1 && (phase == SQPQP_PHASE_FR ? h->has_ilv_fr : h->has_ilv);
+        if (use_ilv) {  // G instances interleaved per CTA (ilv.cuh); flags what it cannot finish for the ADMM launch below
+            CUDA_OK(launch_ilv(h, O, phase, phase == SQPQP_PHASE_FR ? h->ilv_fr : h->ilv, phase == SQPQP_PHASE_FR ? h->ilv_fr_dyn : h->ilv_dyn));
+            h->launches++;
+            h->last_kernel = "k_solve_ilv<" + std::to_string(h->G) + "," + std::to_string(h->ilv_nt) + "," + std::to_string(h->ilv_minb) + ">";
+        } else if (ipm) {
+            launch(1);
+            h->last_kernel = cfg == 4 ? "k_solve_cta<256,4,1>" : (cfg == 2 ? (threads <= 384 ? "k_solve_cta<384,2,1>" : "k_solve_cta<512,2,1>") : "k_solve_cta<512,1,1>");
+        } else h->last_kernel = "k_solve_cta<..,2> (ADMM)";
         else CUDA_OK(cudaMemsetAsync(P.fb_flag, 1, B * sizeof(int), h->stream));  // no factorisation available: every instance
                                                                                   // is "flagged" (non-zero) for the ADMM launch
         if (h->opts.method != 2) launch(2);

@@ -41,7 +41,7 @@ def _ninf(v):
 
 class BatchSqpTR:
     def __init__(self, nlp, batch: int, params: Parameters | None = None, device: int = 0,
-                 engine_options: dict | None = None, x0=None, device_evaluator: bool = False):
+                 engine_options: dict | None = None, x0=None, device_evaluator: bool = False, layout: dict | None = None):
         self.problem = nlp
         self.options = params or Parameters()
         self.B = B = batch
@@ -74,7 +74,7 @@ class BatchSqpTR:
         self.ret = np.full(B, -5, np.int64)
         self.done = np.zeros(B, bool)
         self.n_qp = np.zeros(B, np.int64)
-        self.optimizer = QpDevice(nlp, batch=B, device=device, engine_options=engine_options)
+        self.optimizer = QpDevice(nlp, batch=B, device=device, engine_options=engine_options, layout=layout)
         self.optimizer.create_model(None)
         # f, grad f, g and the J / H COO values evaluated on the device (csrc/acopf.cuh) instead of by the
         # host callbacks -- only x and lambda go up, only f, E, grad f come back

@@ -29,12 +29,14 @@ INFEASIBLE_STATUSES = (capi.MOI_INFEASIBLE, capi.MOI_LOCALLY_INFEASIBLE)
 
 
 class QpDevice:
-    def __init__(self, nlp, batch: int = 1, device: int = 0, engine_options: dict | None = None):
+    def __init__(self, nlp, batch: int = 1, device: int = 0, engine_options: dict | None = None, layout: dict | None = None):
         self.nlp = nlp
         self.batch = batch
         self.engine = capi.Engine(device)
         if engine_options:
             self.engine.set_options(**engine_options)
+        if layout:
+            self.engine.set_layout(**layout)
         self.created = False
         self.stats = {"solves": 0, "instance_solves": 0, "admm_iters": 0, "cg_iters": 0, "polish_cg_iters": 0,
                       "checks": 0, "solve_ms": 0.0, "polished": 0}
