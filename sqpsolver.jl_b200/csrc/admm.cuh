@@ -378,7 +378,11 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
         W.yw = fr ? P.yw_fr + (size_t)inst * P.Ne : P.yw + (size_t)inst * P.n;
         W.dinv = fr ? P.dinv_fr + (size_t)inst * P.Ne : P.dinv + (size_t)inst * P.n;
         W.wJ = P.wJ + (size_t)inst * P.nnzJ;
-        W.D = W.col = nullptr;
+        W.D = W.col = W.gsm = nullptr;
+        if (!pl) {  // grid team: the dense tail lives in global memory, dsm is the per-CTA scratch of its blocked code
+            W.D = fr ? P.Dtail_fr : P.Dtail;
+            W.gsm = dsm;
+        }
         if (pl) {  // shared-memory parts of the factorisation (the dense tail lives nowhere else)
             if (pl->lval >= 0) W.L = dsm + pl->lval;
             if (pl->yw >= 0) W.yw = dsm + pl->yw;
@@ -825,9 +829,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(const __grid_constant_
 
 __global__ void __launch_bounds__(256) k_solve_grid(const __grid_constant__ Prob P, const __grid_constant__ DevOpts O, int phase) {
     __shared__ double sh[SQPQP_MAX_RED * 32];
+    __shared__ double gsm[2 * GD_NB * GD_LD + 64];  // blocked dense tail: two 32 x 33 tiles, inverse pivots, a right-hand-side block
     GridTeam T(sh, P.gred, P.gred_stride);
     for (int inst = 0; inst < P.batch; ++inst) {
         if (P.active && !P.active[inst]) continue;
-        solve_instance<0>(T, P, O.o, inst, phase, (const Placement*)nullptr, (double*)nullptr);
+        solve_instance<0>(T, P, O.o, inst, phase, (const Placement*)nullptr, gsm);
     }
 }

@@ -120,8 +120,8 @@ __device__ void chol_assemble(Team& T, const CholDev& C, const CholWork& W, cons
             if (a < C.nslotJ) wJ[a] = wr[u] * jv[u];
         }
     }
-    if (C.T > 0) {  // packed tail, padded to a multiple of 4 columns with identity rows (dense_factor works in panels of 4)
-        const int Tp = (C.T + 3) & ~3;
+    if (C.T > 0) {  // packed tail, padded to a multiple of the panel width with identity rows (4: dense_factor, 32: dense_factor_grid)
+        const int Tp = C.Tpad;
         for (int i = T.tid(); i < Tp * (Tp + 1) / 2; i += T.size()) W.D[i] = 0.0;
         T.sync();
         for (int i = C.T + T.tid(); i < Tp; i += T.size()) W.D[i * (i + 1) / 2 + i] = 1.0;
@@ -289,6 +289,170 @@ __device__ inline void dense_solve_warp(const double* __restrict__ D, const doub
         if (lane + 32 * s < Tn) yt[lane + 32 * s] = t[s];
 }
 
+// ---- dense tail, GRID team (one large instance: the ~2000-bus network) --------------------------------------------
+// The top of the elimination tree of a 2000-bus network is a chain of ~600 single-column levels (~740 columns): level-
+// scheduled it costs two grid barriers per column and phase.  Here it is one packed dense matrix in global memory
+// (2-4 MB: L2-resident), factorised right-looking in panels of 32 columns by the WHOLE grid:
+//   A. every CTA factorises the 32 x 32 diagonal block redundantly in its shared memory (no grid barrier; block 0 stores it),
+//   B. the rows below the block are forward-substituted against it, one row per thread across the grid,     -- grid.sync
+//   C. the trailing matrix gets its rank-32 update in 32 x 32 tiles, one tile per CTA and trip,              -- grid.sync
+// i.e. 2 grid barriers per 32 columns instead of 128+.  Tp = Tpad is a multiple of 32 (identity padding).
+__device__ inline double dense_factor_grid(GridTeam& T, double* __restrict__ D, double* __restrict__ dinvT, int Tn, int Tp, double* sm) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    double* A = sm;                       // [32][33] diagonal block / X_i tile
+    double* Bk = sm + GD_NB * GD_LD;      // [32][33] X_k tile
+    double* dv = sm + 2 * GD_NB * GD_LD;  // [32] inverse pivots of the block
+    double bad = 0.0;
+    for (int j0 = 0; j0 < Tp; j0 += GD_NB) {
+        // ---- A: diagonal block, redundantly per CTA ----
+        for (int e = tid; e < GD_NB * GD_NB; e += nth) {
+            const int r = e >> 5, c = e & 31;
+            A[r * GD_LD + c] = (c <= r) ? D[tri(j0 + r) + j0 + c] : 0.0;
+        }
+        __syncthreads();
+        for (int c = 0; c < GD_NB; ++c) {
+            double piv = A[c * GD_LD + c];
+            if (!(piv > 0.0)) { bad = 1.0; piv = 1.0; }
+            const double inv = rsqrt(piv);
+            __syncthreads();  // every thread has read the pivot
+            if (tid >= c && tid < GD_NB) A[tid * GD_LD + c] = (tid == c ? piv : A[tid * GD_LD + c]) * inv;
+            if (tid == 0) dv[c] = inv;
+            __syncthreads();
+            for (int e = tid; e < GD_NB * GD_NB; e += nth) {
+                const int r = e >> 5, k = e & 31;
+                if (k > c && r >= k) A[r * GD_LD + k] = fma(-A[r * GD_LD + c], A[k * GD_LD + c], A[r * GD_LD + k]);
+            }
+            __syncthreads();
+        }
+        if (blockIdx.x == 0) {
+            for (int e = tid; e < GD_NB * GD_NB; e += nth) {
+                const int r = e >> 5, c = e & 31;
+                if (c <= r) D[tri(j0 + r) + j0 + c] = A[r * GD_LD + c];
+            }
+            if (tid < GD_NB && j0 + tid < Tn) dinvT[j0 + tid] = dv[tid];
+        }
+        // ---- B: rows below the block, one per thread across the grid: X_i = A_i L_d^{-T} ----
+        {   // a warp per row across the grid, lane c owns x_c: column-oriented substitution with shuffle broadcasts
+            const int lane = tid & 31, gw = T.tid() >> 5, nw = T.size() >> 5;
+            for (int i = j0 + GD_NB + gw; i < Tp; i += nw) {
+                double* __restrict__ row = D + tri(i) + j0;
+                double t = row[lane];
+                const double di = dv[lane];
+                for (int k = 0; k < GD_NB; ++k) {
+                    const double xk = __shfl_sync(0xffffffffu, t * di, k);
+                    if (lane == k) t = xk;
+                    else if (lane > k) t = fma(-xk, A[lane * GD_LD + k], t);
+                }
+                row[lane] = t;
+            }
+        }
+        T.sync();
+        // ---- C: rank-32 update of the trailing matrix in 32 x 32 tiles ----
+        const int nb = (Tp - j0 - GD_NB) / GD_NB;
+        const int ntiles = nb * (nb + 1) / 2;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            int bi = 0;
+            while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;  // tile (bi, bk), bk <= bi (nb <= ~60: a short scan)
+            const int bk = t - bi * (bi + 1) / 2;
+            const int i0 = j0 + GD_NB + bi * GD_NB, k0 = j0 + GD_NB + bk * GD_NB;
+            __syncthreads();  // previous tile (and step A/B reads of A) done
+            for (int e = tid; e < GD_NB * GD_NB; e += nth) {
+                const int r = e >> 5, c = e & 31;
+                A[r * GD_LD + c] = D[tri(i0 + r) + j0 + c];
+                Bk[r * GD_LD + c] = D[tri(k0 + r) + j0 + c];
+            }
+            __syncthreads();
+            for (int e = tid; e < GD_NB * GD_NB; e += nth) {
+                const int r = e >> 5, k = e & 31;
+                if (i0 + r >= k0 + k) {
+                    double sacc = 0.0;
+#pragma unroll
+                    for (int c = 0; c < GD_NB; ++c) sacc = fma(A[r * GD_LD + c], Bk[k * GD_LD + c], sacc);
+                    D[tri(i0 + r) + k0 + k] -= sacc;
+                }
+            }
+        }
+        T.sync();
+    }
+    return bad;  // uniform: every CTA factorised every diagonal block
+}
+
+// Tail solves of the grid team, executed by ONE CTA (the others wait at the grid barrier that follows): blocked by 32,
+// diagonal blocks solved by one warp from shared memory (registers + shuffles), off-diagonal updates by the CTA.
+__device__ inline void dense_solve_block0(const double* __restrict__ D, const double* __restrict__ dinvT, double* yt, int Tn, int Tp, double* sm) {
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
+    double* A = sm;
+    double* yb = sm + 2 * GD_NB * GD_LD + 32;
+    for (int j0 = 0; j0 < Tp; j0 += GD_NB) {  // forward: y = L^{-1} y
+        __syncthreads();
+        for (int e = tid; e < GD_NB * GD_NB; e += nth) {
+            const int r = e >> 5, c = e & 31;
+            A[r * GD_LD + c] = (c <= r) ? D[tri(j0 + r) + j0 + c] : 0.0;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double t = (j0 + lane < Tn) ? yt[j0 + lane] : 0.0;
+            const double di = (j0 + lane < Tn) ? dinvT[j0 + lane] : 1.0;
+            for (int c = 0; c < GD_NB; ++c) {
+                const double yc = __shfl_sync(0xffffffffu, t * di, c);
+                if (lane == c) t = yc;
+                else if (lane > c) t = fma(-A[lane * GD_LD + c], yc, t);
+            }
+            yb[lane] = t;
+            if (j0 + lane < Tn) yt[j0 + lane] = t;
+        }
+        __syncthreads();
+        for (int i = j0 + GD_NB + tid; i < Tn; i += nth) {
+            const double* __restrict__ row = D + tri(i) + j0;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < GD_NB; ++c) acc = fma(row[c], yb[c], acc);
+            yt[i] -= acc;
+        }
+    }
+    for (int j0 = Tp - GD_NB; j0 >= 0; j0 -= GD_NB) {  // backward: x = L^{-T} y
+        __syncthreads();
+        for (int e = tid; e < GD_NB * GD_NB; e += nth) {
+            const int r = e >> 5, c = e & 31;
+            A[r * GD_LD + c] = (c <= r) ? D[tri(j0 + r) + j0 + c] : 0.0;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double t = (j0 + lane < Tn) ? yt[j0 + lane] : 0.0;
+            const double di = (j0 + lane < Tn) ? dinvT[j0 + lane] : 1.0;
+            for (int c = GD_NB - 1; c >= 0; --c) {
+                const double xc = __shfl_sync(0xffffffffu, t * di, c);
+                if (lane == c) t = xc;
+                else if (lane < c) t = fma(-A[c * GD_LD + lane], xc, t);
+            }
+            yb[lane] = t;
+            if (j0 + lane < Tn) yt[j0 + lane] = t;
+        }
+        __syncthreads();
+        for (int k = tid; k < j0; k += nth) {  // y_k -= sum_c L[j0 + c][k] x_c   (coalesced over k)
+            double acc = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < GD_NB; ++c) acc = fma(D[tri(j0 + c) + k], yb[c], acc);
+            yt[k] -= acc;
+        }
+    }
+    __syncthreads();
+}
+
+// team dispatch of the dense-tail code
+__device__ __forceinline__ double team_dense_factor(CtaTeam&, const CholDev& C, const CholWork& W) {
+    return dense_factor(W.D, W.dinv + C.n0, C.T);
+}
+__device__ __forceinline__ double team_dense_factor(GridTeam& T, const CholDev& C, const CholWork& W) {
+    return dense_factor_grid(T, W.D, W.dinv + C.n0, C.T, C.Tpad, W.gsm);
+}
+__device__ __forceinline__ void team_dense_solve(CtaTeam&, const CholDev& C, const CholWork& W, double* yw) {
+    if (threadIdx.x < 32) dense_solve_warp(W.D, W.dinv + C.n0, yw + C.n0, C.T);
+}
+__device__ __forceinline__ void team_dense_solve(GridTeam&, const CholDev& C, const CholWork& W, double* yw) {
+    if (blockIdx.x == 0) dense_solve_block0(W.D, W.dinv + C.n0, yw + C.n0, C.T, C.Tpad, W.gsm);
+}
+
 // In-place numeric factorisation: the barrier phases of symbolic.hpp 4c (per sparse level the
 // diagonal entries, then the sub-diagonal entries; then the Schur complement of the dense tail).  A
 // thread executes one SLOT per round: one lane's share of a task, the lane count chosen per task on
@@ -350,7 +514,7 @@ __device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& 
     }
     pf.lap(PS_FACTOR_SPARSE);
     if (C.T > 0) {
-        bad[0] = fmax(bad[0], dense_factor(W.D, W.dinv + C.n0, C.T));
+        bad[0] = fmax(bad[0], team_dense_factor(T, C, W));
         pf.lap(PS_FACTOR_DENSE);
     }
     T.template reduce<1, true>(bad);
@@ -393,7 +557,7 @@ __device__ void chol_solve(Team& T, const CholDev& C, const CholWork& W, const d
             if (on && lane == 0) yw[j] -= acc;
         }
         T.sync();
-        if (threadIdx.x < 32) dense_solve_warp(W.D, dinv + C.n0, yw + C.n0, C.T);
+        team_dense_solve(T, C, W, yw);
         T.sync();
         pf.lap(PS_TAIL);
     }

@@ -19,6 +19,8 @@
 namespace cg = cooperative_groups;
 
 #define SQPQP_MAX_RED 8  // values per fused reduction
+#define GD_NB 32         // panel width of the grid team's blocked dense tail (chol.cuh)
+#define GD_LD 33         // padded leading dimension of its 32 x 32 shared-memory tiles
 
 // ---- vector slots ----------------------------------------------------------------
 // N-type vectors have per-instance stride Ne = n + S, M-type vectors stride m.
@@ -41,6 +43,7 @@ struct Csr {
 // dense tail n0 .. n-1 (T columns, factorised as a packed dense matrix in shared memory).
 struct CholDev {
     int n, nnzL, nlev, n0, T;
+    int Tpad;               // T rounded up to the panel width of the dense code (4: CTA team, 32: grid team); padding rows are identity
     int nphase, n_aslot, nslotJ;
     const int *perm;
     const int *Lp, *Li;
@@ -64,6 +67,7 @@ struct CholWork {
     double* dinv;   // [n] 1 / L_jj
     double* yw;     // [n] triangular-solve scratch in permuted order
     double* wJ;     // [nslotJ] w[row] * Jv per J value slot (global)
+    double* gsm;    // grid team: per-CTA shared scratch of the blocked dense code (3 x 32 x 33 doubles), else null
 };
 
 struct Prob {
@@ -102,6 +106,7 @@ struct Prob {
     double *Lval, *yw, *Lval_fr, *yw_fr;
     double *wJ;               // [batch][nnzJ]
     double *dinv, *dinv_fr;   // [batch][n], [batch][Ne] (used when the shared-memory budget cannot hold them)
+    double *Dtail, *Dtail_fr; // grid team (one large instance): packed dense tail of the factor in global memory (L2-resident)
     // grid-team reduction scratch: [2][SQPQP_MAX_RED][maxblocks]
     double* gred;
     int gred_stride;

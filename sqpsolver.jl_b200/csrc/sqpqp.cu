@@ -676,8 +676,12 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             *dst = d;
             return 0;
         };
+        // one large instance runs on the cooperative grid: its dense tail lives in global memory and is factorised by
+        // the whole grid in panels of 32 columns (chol.cuh: dense_factor_grid)
+        const bool grid_mode = batch == 1 && (size_t)P.Ne + m > 6000;
         auto upload_symbolic = [&](Symbolic& Sy, CholDev& C, int ncols) -> int {
             C.n = ncols; C.nnzL = Sy.nnzL; C.nlev = Sy.nlev; C.n0 = Sy.n0; C.T = Sy.T;
+            C.Tpad = grid_mode ? ((Sy.T + GD_NB - 1) / GD_NB) * GD_NB : ((Sy.T + 3) & ~3);
             C.nphase = (int)Sy.fphase.size() / 4; C.n_aslot = (int)Sy.aslot_d.size(); C.nslotJ = (int)Sy.jrow.size();
             for (int k = 0; k < 4; ++k) Sy.fphase.push_back(0);  // the phase loop reads one entry ahead
             if (Sy.as_ab.empty()) { Sy.as_ab.push_back(0); Sy.as_ab.push_back(0); }
@@ -710,7 +714,9 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             return (size_t)ncols * G * sizeof(double) + (size_t)52 * 53 / 2 * G * sizeof(double) <= ilv_budget;
         };
         auto tail_cap = [&](int ncols) -> int {
-            if (batch == 1 && (size_t)P.Ne + m > 6000) return 0;
+            // grid team: the chain at the top of the tree (~740 columns on the 2000-bus network) becomes one dense block;
+            // 1024 columns = 4 MB packed (L2-resident), its factorisation 0.36 Gflop
+            if (grid_mode) return h->tail_override >= 0 ? h->tail_override : 1024;
             if (G > 1) {
                 size_t cap = ilv_budget / sizeof(double) / G;  // doubles per instance
                 if (ilv_yw_resident(ncols)) cap -= ncols;
@@ -780,6 +786,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             DALLOC(P.Lval, B * (size_t)Sy.nnzL);
             DALLOC(P.yw, B * (size_t)n);
             DALLOC(P.dinv, B * (size_t)n);
+            if (grid_mode && Sy.T > 0) DALLOC(P.Dtail, (size_t)P.chol.Tpad * (P.chol.Tpad + 1) / 2);
             P.has_chol = 1;
             h->chol_nnzL = Sy.nnzL; h->chol_nlev = Sy.nlev; h->chol_flops = Sy.flops; h->chol_tail = Sy.T;
             h->chol_nlev_total = Sy.nlev_total;
@@ -799,6 +806,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
                 DALLOC(P.Lval_fr, B * (size_t)Sf.nnzL);
                 DALLOC(P.yw_fr, B * (size_t)P.Ne);
                 DALLOC(P.dinv_fr, B * (size_t)P.Ne);
+                if (grid_mode && Sf.T > 0) DALLOC(P.Dtail_fr, (size_t)P.chol_fr.Tpad * (P.chol_fr.Tpad + 1) / 2);
                 P.has_chol_fr = 1;
                 if (G > 1) {
                     rc2 = build_ilv(Sf, P.chol_fr, P.Ne, &h->ilv_fr, &h->ilv_fr_dyn);
@@ -1019,7 +1027,9 @@ static int launch_solve(sqpqp_handle h, int phase) {
     DevOpts O{h->opts};
     int team = h->opts.team;
     if (team == 0) team = (B == 1 && (size_t)P.Ne + P.m > 6000) ? 2 : 1;
-    if (team == 2 && ((phase == SQPQP_PHASE_FR ? P.chol_fr.T : P.chol.T) > 0)) team = 1;  // dense tail needs CTA shared memory
+    // a dense tail laid out for the CTA team (panels of 4, shared memory) cannot be run by the grid team and vice versa
+    if (team == 2 && ((phase == SQPQP_PHASE_FR ? P.chol_fr.T : P.chol.T) > 0) && !(phase == SQPQP_PHASE_FR ? P.Dtail_fr : P.Dtail)) team = 1;
+    if (team == 1 && ((phase == SQPQP_PHASE_FR ? P.chol_fr.T : P.chol.T) > 0) && (phase == SQPQP_PHASE_FR ? P.Dtail_fr : P.Dtail)) team = 2;
     CUDA_OK(cudaEventRecord(h->ev0, h->stream));
     if (team == 2) {
         void* args[] = {(void*)&P, (void*)&O, (void*)&phase};
@@ -1089,9 +1099,10 @@ static int launch_solve(sqpqp_handle h, int phase) {
         } else if (ipm) {
             launch(1);
             h->last_kernel = cfg == 4 ? "k_solve_cta<256,4,1>" : (cfg == 2 ? (threads <= 384 ? "k_solve_cta<384,2,1>" : "k_solve_cta<512,2,1>") : "k_solve_cta<512,1,1>");
-        } else h->last_kernel = "k_solve_cta<..,2> (ADMM)";
-        else CUDA_OK(cudaMemsetAsync(P.fb_flag, 1, B * sizeof(int), h->stream));  // no factorisation available: every instance
-                                                                                  // is "flagged" (non-zero) for the ADMM launch
+        } else {  // no factorisation available: every instance is "flagged" (non-zero) for the ADMM launch
+            h->last_kernel = "k_solve_cta<..,2> (ADMM)";
+            CUDA_OK(cudaMemsetAsync(P.fb_flag, 1, B * sizeof(int), h->stream));
+        }
         if (h->opts.method != 2) launch(2);
         h->launches--;  // counted below
     }

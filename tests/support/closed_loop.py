@@ -109,9 +109,12 @@ def check_trace(nlp, trace, oracle_every=1, marginal=1e-6, qp_tol=1e-10, verbose
             out["infeasible"] += 1
             assert not t["p"].any() and not t["lambda_qp"].any(), ("zero fill", k)  # collect_solution! :551-555
             if qs.is_feasible(A, rl, ru, xl, xu):
+                # HiGHS did not certify infeasibility (on the 2000-bus network it can also stop without a verdict): measure
+                # how far from feasible the constraint set is.  Clearly positive -> infeasible, the device is right;
+                # below `marginal` -> a marginal subproblem the two sides may legitimately classify differently (counted)
                 v = least_l1_violation(A, rl, ru, xl, xu)
-                assert v <= marginal, ("device infeasible, oracle feasible", k, v)
-                out["marginal_mismatch"] += 1
+                if v <= marginal:
+                    out["marginal_mismatch"] += 1
             continue
         assert st in OK, ("QP status", k, st, t["info"])
         out["almost"] += int(st == capi.MOI_ALMOST_LOCALLY_SOLVED)
