@@ -193,8 +193,9 @@ struct IpmOut {
     double rp, rd, rho_p;
 };
 template <class Team>
-__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, const sqpqp_options& o,
+__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, Ring* R, const sqpqp_options& o,
                           double c, int phase, const double* xk_scaled_start);
+__device__ __forceinline__ void ring_init(Ring& R, const CholDev& C, const CholWork& W, int stage0_dbl, unsigned long long* bars);
 
 // ---------------------------------------------------------------------------------------
 // MODE 0: interior point, then the ADMM fallback in the same kernel (cooperative-grid team).
@@ -215,7 +216,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
 
 template <int MODE, class Team>
 __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, int inst, int phase,
-                               const Placement* pl, double* dsm) {
+                               const Placement* pl, double* dsm, unsigned long long* rbar = nullptr) {
     if constexpr (MODE == 2) {
         if (o.method != 1 && P.fb_flag[inst] == 0) return;  // uniform per team: solved by the interior-point launch
     }
@@ -396,8 +397,15 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
             T.sync();
             start = x;
         }
+        Ring R;
+        R.on = false;
+        W.oL = W.oyw = W.odinv = W.oD = -1;
+        if (pl && rbar && pl->ring >= 0 && CD.ring_ok) {  // ring mode: L, yw, dinv (and the tail) are in shared memory (launch_solve)
+            W.oL = pl->lval; W.oyw = pl->yw; W.odinv = pl->dinv; W.oD = pl->dtail >= 0 ? pl->dtail : 0;
+            ring_init(R, CD, W, pl->ring, rbar);
+        }
         pfo.lap(PS_PROLOGUE);
-        IpmOut io = ipm_run(T, I, CD, W, o, c, phase, start);
+        IpmOut io = ipm_run(T, I, CD, W, R.on ? &R : (Ring*)nullptr, o, c, phase, start);
         pfo.start();
         ipm_iters = io.iters;
         nfact = io.nfact;
@@ -818,11 +826,12 @@ template <int MAXT, int MINB, int MODE>
 __global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(const __grid_constant__ Prob P, const __grid_constant__ DevOpts O, int phase,
                                                           const __grid_constant__ Placement pl) {
     __shared__ double sh[2 * SQPQP_MAX_RED * 32];
+    __shared__ unsigned long long rbar[RING_S];  // mbarriers of the index-program ring (chol.cuh)
     extern __shared__ double dsm[];
     for (int inst = blockIdx.x; inst < P.batch; inst += gridDim.x) {
         if (P.active && !P.active[inst]) continue;
         CtaTeam T(sh);
-        solve_instance<MODE>(T, P, O.o, inst, phase, &pl, dsm);
+        solve_instance<MODE>(T, P, O.o, inst, phase, &pl, dsm, MODE == 2 ? (unsigned long long*)nullptr : rbar);
         __syncthreads();
     }
 }

@@ -91,6 +91,185 @@ __device__ __forceinline__ void gather_dot2(const int2* __restrict__ ab, int qa,
     rb = b0 + b1;
 }
 
+
+// ---- shared-memory ring of index-program chunks (resident CTA team) ----------------------------------------------------
+// One CTA owns an SM and keeps L, the dense tail, the solve scratch and the gathered vectors in shared memory; what is
+// left on the critical path of a barrier phase of the slot-list code above is the L2 round trip of its index program
+// (slot -> pair list, ~3 000 cycles per phase measured).  The program is static, so symbolic.hpp lays it out as
+// self-contained chunk images and thread 0 streams them into RING_S shared-memory stages with bulk asynchronous copies
+// (cp.async.bulk, completion on an mbarrier) RING_S - 1 chunks ahead of the consumers.  A chunk is one strip of slots of one
+// barrier phase; every chunk ends with the __syncthreads the phase needs anyway, which is also what frees its stage.
+extern __shared__ double ring_sm[];  // the CTA's dynamic shared memory (same base as dsm in k_solve_cta): shared-space loads
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_init(Ring& R, const CholDev& C, const CholWork& W, int stage0_dbl, unsigned long long* bars) {
+    R.prog = C.rprog; R.stage0w = 2 * stage0_dbl; R.stage_words = C.ring_stage_words; R.bar0 = smem_u32(bars);
+    R.phase_bits = 0; R.head = 0; R.inflight = 0; R.seg = -1; R.on = true;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < RING_S; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(R.bar0 + 8 * s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ring_sm[W.oL + C.ring_nL] = 0.0;  // the zero entry short pair lists are padded with
+    }
+    __syncthreads();
+}
+// thread 0 only: bulk copy of one chunk image into a stage, completion (byte count) on the stage's barrier
+__device__ __forceinline__ void ring_issue(const Ring& R, int stage, int word_off, int bytes) {
+    const unsigned bar = R.bar0 + 8 * stage;
+    const unsigned dst = smem_u32(reinterpret_cast<const int*>(ring_sm) + R.stage0w + stage * R.stage_words);
+    const int* src = R.prog + word_off;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ring_wait_stage(Ring& R, int stage) {
+    const unsigned bar = R.bar0 + 8 * stage, par = (R.phase_bits >> stage) & 1u;
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(par) : "memory");
+    }
+    R.phase_bits ^= 1u << stage;
+}
+// Make `seg` the segment whose first chunks are in flight.  Called by all threads, after a barrier that follows the last
+// read of any stage.  A segment primed earlier but not wanted is drained first: a bulk copy cannot be cancelled.
+__device__ __forceinline__ void ring_prime(Ring& R, const CholDev& C, int seg) {
+    if (R.seg == seg && R.head == 0 && R.inflight > 0) return;
+    if (R.inflight > 0) {  // (uniform) every thread must have seen these phases complete before their barriers are re-armed
+        for (int i = 0; i < R.inflight; ++i) ring_wait_stage(R, (R.head + i) % RING_S);
+        __syncthreads();
+    }
+    const int cnt = C.rseg_n[seg] < RING_S ? C.rseg_n[seg] : RING_S;
+    if (threadIdx.x == 0)
+        for (int s = 0; s < cnt; ++s) ring_issue(R, s, C.rseg_off[seg][s], C.rseg_bytes[seg][s]);
+    R.seg = seg; R.head = 0; R.inflight = cnt;
+}
+__device__ __forceinline__ void ring_drain(Ring& R) {
+    for (int i = 0; i < R.inflight; ++i) ring_wait_stage(R, (R.head + i) % RING_S);
+    R.inflight = 0; R.head = 0; R.seg = -1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < RING_S; ++s) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(R.bar0 + 8 * s));
+    }
+    R.on = false;
+}
+
+struct RingArgs {
+    const double* Pv;   // scaled P values or null
+    const double* dg;   // diagonal term per ORIGINAL column
+    double shift;       // inertia shift added to every diagonal entry
+    const double* Jv;   // scaled J values (assembly)
+};
+// One segment of the ring program (symbolic.hpp: kinds 0..6).  Returns 1.0 if a diagonal pivot was not positive (per thread;
+// the caller reduces).  `next_seg` >= 0: its first chunks are requested as soon as the last stage of this segment is free.
+// Factor / sweep chunks read L, yw, dinv, D and the chunk itself through the shared window (32-bit addresses, no
+// predicates: short pair lists multiply the zero entry); assembly chunks gather wJ and Jv from global memory.
+// The ring state and the work pointers are copied into locals for the duration of the segment (both structs live in the
+// caller's frame; behind a reference every asm with a memory clobber would force their fields to be re-read).
+__device__ __forceinline__ double ring_run_segment(Ring& Rref, const CholDev& C, const CholWork& Wref, int seg, int next_seg,
+                                                   const RingArgs& aref, Prof& pf) {
+    Ring R = Rref;
+    const CholWork W = Wref;
+    const RingArgs a = aref;
+    ring_prime(R, C, seg);
+    double bad = 0.0;
+    int prev_asm = 0;
+    const int* smw = reinterpret_cast<const int*>(ring_sm);
+    const int oL = W.oL, oyw = W.oyw, odinv = W.odinv, oD = W.oD;
+    for (;;) {
+        const int stage = R.head % RING_S;
+        const long long c0 = SQPQP_CLK();
+        ring_wait_stage(R, stage);
+        const long long c1 = SQPQP_CLK();
+        const int* img = smw + R.stage0w + stage * R.stage_words;
+        const int npad = img[0], kmax = img[1], is_asm = img[2], last = img[3], nxo = img[4], nxb = img[5];
+        if (prev_asm && !is_asm) pf.lap(PS_ASSEMBLE_SLOTS);
+        prev_asm = is_asm;
+        const int2* slots = reinterpret_cast<const int2*>(img + 8);
+        if (!is_asm) {
+            for (int s = threadIdx.x; s < npad; s += blockDim.x) {  // whole warps: npad and blockDim are multiples of 32
+                const int2 sl = slots[s];
+                const int* pw = img + 8 + 2 * npad + s;
+                const int tgt = sl.x & 0xffff, lgv = (sl.x >> 16) & 7, kind = (sl.x >> 28) & 7;
+                const bool leader = (sl.x >> 19) & 1;
+                const int oB = kind >= 3 ? oyw : oL;
+                // operands of the finalisation that do not depend on the sum: issued before the gathers
+                double f0 = 0.0, f1 = 1.0;
+                if (leader) {
+                    if (kind <= 1) { if ((sl.x >> 20) & 1) f0 = ring_sm[oL + tgt]; if (kind == 1) f1 = ring_sm[odinv + sl.y]; }
+                    else if (kind == 2) f0 = ring_sm[oD + sl.y];
+                    else { f0 = ring_sm[oyw + tgt]; if (kind == 3) f1 = ring_sm[odinv + tgt]; }
+                }
+                double acc0 = 0.0, acc1 = 0.0;
+                for (int k = 0; k < kmax; k += 2) {
+                    const unsigned p0 = (unsigned)pw[k * npad], p1 = (unsigned)pw[(k + 1) * npad];
+                    acc0 = fma(ring_sm[oL + (p0 & 0xffffu)], ring_sm[oB + (p0 >> 16)], acc0);
+                    acc1 = fma(ring_sm[oL + (p1 & 0xffffu)], ring_sm[oB + (p1 >> 16)], acc1);
+                }
+                double acc = acc0 + acc1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {  // lane groups of mixed (power of two, aligned) sizes share the butterfly
+                    const double t = __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (o < (1 << lgv)) acc += t;
+                }
+                if (leader) {
+                    double v = f0 - acc;
+                    if (kind == 0) {
+                        if (!(v > 0.0)) { bad = 1.0; v = 1.0; }
+                        const double inv = rsqrt(v);
+                        ring_sm[oL + tgt] = v * inv;
+                        ring_sm[odinv + sl.y] = inv;
+                    } else if (kind == 1) ring_sm[oL + tgt] = v * f1;
+                    else if (kind == 2) ring_sm[oD + sl.y] = v;
+                    else ring_sm[oyw + tgt] = v * f1;  // kind 3: scaled by the pivot; kind 4: f1 = 1
+                }
+            }
+        } else {
+            for (int s = threadIdx.x; s < npad; s += blockDim.x) {
+                const int2 sl = slots[s];
+                const int* pw = img + 8 + 2 * npad + s;
+                const int tgt = sl.x & 0xffff, lgv = (sl.x >> 16) & 7, ks = (sl.x >> 21) & 0x7f, kind = (sl.x >> 28) & 7;
+                const bool leader = (sl.x >> 19) & 1;
+                double f0 = 0.0;
+                if (leader) {
+                    const int h = (sl.y & 0xffff) - 1, d = (int)((unsigned)sl.y >> 16) - 1;
+                    if (a.Pv && h >= 0) f0 = a.Pv[h];
+                    if (d >= 0) f0 += a.dg[d] + a.shift;
+                }
+                double acc0 = 0.0, acc1 = 0.0;
+                for (int k = 0; k < kmax; k += 2) {
+                    const unsigned p0 = (unsigned)pw[k * npad], p1 = (unsigned)pw[(k + 1) * npad];
+                    const bool o0 = k < ks, o1 = k + 1 < ks;
+                    const double a0 = W.wJ[o0 ? (p0 & 0xffffu) : 0u], b0 = a.Jv[o0 ? (p0 >> 16) : 0u];
+                    const double a1 = W.wJ[o1 ? (p1 & 0xffffu) : 0u], b1 = a.Jv[o1 ? (p1 >> 16) : 0u];
+                    if (o0) acc0 = fma(a0, b0, acc0);
+                    if (o1) acc1 = fma(a1, b1, acc1);
+                }
+                double acc = acc0 + acc1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double t = __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (o < (1 << lgv)) acc += t;
+                }
+                if (leader) ring_sm[(kind == 5 ? oL : oD) + tgt] = f0 + acc;
+            }
+        }
+        const long long c2 = SQPQP_CLK();
+        __syncthreads();  // the phase barrier; every thread is done with this stage
+        const long long c3 = SQPQP_CLK();
+        pf.add(PS_RING_WAIT, c1 - c0); pf.add(PS_RING_WORK, c2 - c1); pf.add(PS_RING_BAR, c3 - c2); pf.add(PS_RING_CHUNKS, 1);
+        pf.add(20 + is_asm, c2 - c1);  // (profile builds) work cycles: factor / sweep chunks, assembly chunks
+        if (nxo >= 0) { if (threadIdx.x == 0) ring_issue(R, stage, nxo, nxb); }
+        else --R.inflight;
+        ++R.head;
+        if (last) break;
+    }
+    R.seg = -1; R.head = 0;  // (inflight is 0 here: the chunks without a successor each gave one back)
+    if (next_seg >= 0) ring_prime(R, C, next_seg);
+    Rref = R;
+    return bad;
+}
+
 // L <- lower triangle of K in the permuted order, sourced entries only (pure fill entries have
 // K_e = 0 and are never read: their factor task carries has_K = 0).  Pv may be null (no P); dg[j] + shift
 // is added to the diagonal entry of ORIGINAL column j.  Also clears the dense tail.
@@ -575,6 +754,71 @@ __device__ void chol_solve(Team& T, const CholDev& C, const CholWork& W, const d
         }
         T.sync();
     }
+    for (int k = T.tid(); k < C.n; k += T.size()) x[C.perm[k]] = yw[k];
+    T.sync();
+    pf.lap(PS_BWD);
+}
+
+// ---- resident CTA team: the same factorisation and solves driven by the ring program ---------------------------------------
+// Assembly (wJ pre-pass and tail clear as in chol_assemble, then the assembly chunks), the sparse levels WITH the forward
+// sweep of right-hand side b riding in their chunks, and the Schur complement with the tail right-hand side are ONE segment,
+// so the stream never stops between them; the backward sweep is requested while the dense tail is being factorised.
+// The tail block of L is not used in this mode: its assembled K goes straight into D.
+__device__ __forceinline__ bool chol_assemble_factor_fwd_ring(CtaTeam& T, Ring& R, const CholDev& C, const CholWork& W,
+                                                              const double* __restrict__ Pv, const double* __restrict__ dg,
+                                                              const double shift, const double* __restrict__ w,
+                                                              const double* __restrict__ Jv, const double* __restrict__ b, Prof& pf) {
+    ring_prime(R, C, 0);  // in flight while wJ is formed
+    double* wJ = W.wJ;
+    for (int a0 = T.tid(); a0 < C.nslotJ; a0 += 4 * T.size()) {
+        int r[4];
+        double jv[4], wr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * T.size();
+            const bool ok = a < C.nslotJ;
+            r[u] = ok ? C.jrow[a] : -1;
+            jv[u] = ok ? Jv[a] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wr[u] = r[u] >= 0 ? w[r[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u * T.size();
+            if (a < C.nslotJ) wJ[a] = wr[u] * jv[u];
+        }
+    }
+    for (int k = T.tid(); k < C.n; k += T.size()) W.yw[k] = b[C.perm[k]];  // a failed attempt has overwritten it
+    if (C.T > 0) {
+        const int Tp = C.Tpad;
+        for (int i = T.tid(); i < Tp * (Tp + 1) / 2; i += T.size()) W.D[i] = 0.0;
+        T.sync();
+        for (int i = C.T + T.tid(); i < Tp; i += T.size()) W.D[i * (i + 1) / 2 + i] = 1.0;
+    }
+    T.sync();
+    pf.lap(PS_ASSEMBLE);
+    RingArgs a{Pv, dg, shift, Jv};
+    double bad[1];
+    bad[0] = ring_run_segment(R, C, W, 0, 2, a, pf);
+    pf.lap(PS_FACTOR_SPARSE);
+    if (C.T > 0) {
+        bad[0] = fmax(bad[0], dense_factor(W.D, W.dinv + C.n0, C.T));
+        pf.lap(PS_FACTOR_DENSE);
+    }
+    T.template reduce<1, true>(bad);
+    return bad[0] == 0.0;
+}
+
+// the rest of the solve after chol_assemble_factor_fwd_ring: dense tail, backward sweep, x in original order
+__device__ __forceinline__ void chol_backsolve_ring(CtaTeam& T, Ring& R, const CholDev& C, const CholWork& W, double* x, Prof& pf) {
+    double* yw = W.yw;
+    if (C.T > 0) {
+        if (threadIdx.x < 32) dense_solve_warp(W.D, W.dinv + C.n0, yw + C.n0, C.T);
+        T.sync();
+        pf.lap(PS_TAIL);
+    }
+    RingArgs a{nullptr, nullptr, 0.0, nullptr};
+    ring_run_segment(R, C, W, 2, 0, a, pf);
     for (int k = T.tid(); k < C.n; k += T.size()) x[C.perm[k]] = yw[k];
     T.sync();
     pf.lap(PS_BWD);

@@ -21,6 +21,7 @@ namespace cg = cooperative_groups;
 #define SQPQP_MAX_RED 8  // values per fused reduction
 #define GD_NB 32         // panel width of the grid team's blocked dense tail (chol.cuh)
 #define GD_LD 33         // padded leading dimension of its 32 x 32 shared-memory tiles
+#define RING_S 3         // stages of the shared-memory ring the index programs are streamed through (chol.cuh)
 
 // ---- vector slots ----------------------------------------------------------------
 // N-type vectors have per-instance stride Ne = n + S, M-type vectors stride m.
@@ -57,6 +58,12 @@ struct CholDev {
     const int *aslot_d;     // per assembly slot: original column for the diagonal term d[], or -1
     const int2 *as_ab;      // assembly terms (wJ index, Jv index)
     const int *jrow;        // row of every J value slot
+    // ring programs (symbolic.hpp: build_ring_program) for the resident CTA team; ring_ok = 0: not built
+    int ring_ok, ring_nL, ring_stage_words;
+    const int *rprog;                 // chunk images, 16-byte aligned
+    int rseg_n[3];                    // chunks per segment (0 assembly + factor, 1 forward + tail rhs, 2 backward)
+    int rseg_off[3][RING_S];          // word offset of the first RING_S chunks of each segment (-1: none)
+    int rseg_bytes[3][RING_S];
 };
 
 // per-instance numeric state of the factorisation, resolved for one team
@@ -68,6 +75,7 @@ struct CholWork {
     double* yw;     // [n] triangular-solve scratch in permuted order
     double* wJ;     // [nslotJ] w[row] * Jv per J value slot (global)
     double* gsm;    // grid team: per-CTA shared scratch of the blocked dense code (3 x 32 x 33 doubles), else null
+    int oL, oyw, odinv, oD;  // ring mode: the same four arrays as offsets (doubles) into the CTA's dynamic shared memory
 };
 
 struct Prob {
@@ -121,8 +129,22 @@ struct Placement {
     int jsv, tsv, hsv;
     int lval, yw;
     int dtail, dcol, dinv;  // dense tail of the factor, its pivot column, inverse diagonal (interior-point path)
+    int ring;               // RING_S stages of chol.ring_stage_words words for the streamed index programs, or -1 (slot lists from L2)
     int vec_resident;       // 1 if any work vector / matrix value array is placed (else only the factorisation parts)
     int total;  // doubles
+};
+
+// state of the shared-memory ring the index programs are streamed through (chol.cuh); uniform across the CTA
+struct Ring {
+    const int* prog;       // global: chunk images
+    int stage0w;           // first stage as a WORD offset into the CTA's dynamic shared memory (RING_S x stage_words words)
+    int stage_words;
+    unsigned bar0;         // shared address of mbarrier 0 (8 bytes each)
+    unsigned phase_bits;   // expected parity per stage
+    int head;              // chunks of the current segment consumed so far
+    int inflight;          // chunks issued, not yet consumed
+    int seg;               // segment primed or in progress (-1: none)
+    bool on;
 };
 
 // ---- optional in-kernel phase profile (build with -DSQPQP_PROF; tools/gpu_prof.py) ----------------
@@ -130,7 +152,9 @@ struct Placement {
 // table; the sum over CTAs gives the share of CTA-time per segment.  Compiled out by default.
 enum ProfSeg {
     PS_PROLOGUE = 0, PS_RESID, PS_WEIGHTS, PS_ASSEMBLE, PS_FACTOR_SPARSE, PS_ASSEMBLE_SLOTS, PS_FACTOR_DENSE, PS_RHS, PS_FWD, PS_TAIL,
-    PS_BWD, PS_RATIO, PS_UPDATE, PS_EPILOGUE, PS_OTHER, PS_COUNT
+    PS_BWD, PS_RATIO, PS_UPDATE, PS_EPILOGUE, PS_OTHER, PS_COUNT,
+    // ring detail (thread 0; included in the segments above): waiting for a chunk, working on it, at its barrier, chunks
+    PS_RING_WAIT = 16, PS_RING_WORK, PS_RING_BAR, PS_RING_CHUNKS
 };
 #ifdef SQPQP_PROF
 __device__ unsigned long long g_prof[32];
@@ -142,12 +166,18 @@ struct Prof {
         if (threadIdx.x == 0) atomicAdd(&g_prof[k], (unsigned long long)(t - t0));
         t0 = t;
     }
+    __device__ __forceinline__ void add(int k, long long v) {
+        if (threadIdx.x == 0) atomicAdd(&g_prof[k], (unsigned long long)v);
+    }
 };
+#define SQPQP_CLK() clock64()
 #else
 struct Prof {
     __device__ __forceinline__ void start() {}
     __device__ __forceinline__ void lap(int) {}
+    __device__ __forceinline__ void add(int, long long) {}
 };
+#define SQPQP_CLK() 0ll
 #endif
 
 #define CUDA_OK(call)                                                       \

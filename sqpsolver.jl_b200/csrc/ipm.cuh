@@ -33,8 +33,32 @@ __device__ __forceinline__ SideDir side_dir(double rc, double z, double s, doubl
 // largest step fraction bookkeeping: returns max(-dv/v, 0) so that alpha = 1/max(...)
 __device__ __forceinline__ double step_ratio(double v, double dv) { return dv < 0.0 ? -dv / v : 0.0; }
 
+// assembly + factorisation and the Newton solve, by team.  The resident CTA team streams the ring program when it has one:
+// the right-hand side b is then needed BEFORE the factorisation, because its forward sweep rides in the factor chunks.
 template <class Team>
-__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, const sqpqp_options& o,
+__device__ __forceinline__ bool team_assemble_factor(Team& T, Ring*, const CholDev& C, const CholWork& W, const double* Pv, const double* dg,
+                                                     double shift, const double* w, const double* Jv, const double*, Prof& pf) {
+    chol_assemble(T, C, W, Pv, dg, shift, w, Jv, pf);
+    return chol_factor(T, C, W, pf);
+}
+__device__ __forceinline__ bool team_assemble_factor(CtaTeam& T, Ring* R, const CholDev& C, const CholWork& W, const double* Pv,
+                                                     const double* dg, double shift, const double* w, const double* Jv,
+                                                     const double* b, Prof& pf) {
+    if (R) return chol_assemble_factor_fwd_ring(T, *R, C, W, Pv, dg, shift, w, Jv, b, pf);
+    chol_assemble(T, C, W, Pv, dg, shift, w, Jv, pf);
+    return chol_factor(T, C, W, pf);
+}
+template <class Team>
+__device__ __forceinline__ void team_solve(Team& T, Ring*, const CholDev& C, const CholWork& W, const double* b, double* x, Prof& pf) {
+    chol_solve(T, C, W, b, x, pf);
+}
+__device__ __forceinline__ void team_solve(CtaTeam& T, Ring* R, const CholDev& C, const CholWork& W, const double* b, double* x, Prof& pf) {
+    if (R) chol_backsolve_ring(T, *R, C, W, x, pf);
+    else chol_solve(T, C, W, b, x, pf);
+}
+
+template <class Team>
+__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, Ring* R, const sqpqp_options& o,
                           double c, int phase, const double* xk_scaled_start) {
     const int N = I.N, M = I.M;
     // Work vectors are slots of the ADMM workspace (the two methods never run concurrently), addressed through
@@ -257,11 +281,23 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
             else break;
         }
         pf.lap(PS_WEIGHTS);
+        const double sigma_mu = mu_t;
+        const double tau_k = fmax(o.ipm_tau, 1.0 - mu_t);
+        auto build_rhs = [&]() {  // P3 / P4: rhs = -r_x - J' t - t_box with t = sigma*mu * a + b
+            for_n(T, M, [&](int i) { I.mv[M_T][i] = fma(sigma_mu, I.mv[M_YP][i], I.mv[M_TMP][i]); });
+            T.sync();
+            csr_rows(T, N, I.lgT, I.T.rb, I.T.re, I.T.col, I.Tsv, I.mv[M_T], [&](int j, double tt) {
+                const double tb = fma(sigma_mu, I.nv[N_MINV][j], I.nv[N_XFIX][j]);
+                I.nv[N_P][j] = -I.nv[N_R][j] - tt - tb;
+            });
+            T.sync();
+            pf.lap(PS_RHS);
+        };
+        if (R) build_rhs();  // ring mode: the forward sweep of the Newton solve rides in the factorisation's chunks
         // ---- assembly, factorisation (with inertia correction: the shift rho_p is a scalar on the diagonal) ----
         bool fact_ok = false;
         for (int tries = 0; tries < 30 && !fact_ok; ++tries) {
-            chol_assemble(T, C, W, I.useH ? I.Hsv : (const double*)nullptr, I.nv[N_DSH], rho_p, I.mv[M_RW], I.Jsv, pf);
-            fact_ok = chol_factor(T, C, W, pf);
+            fact_ok = team_assemble_factor(T, R, C, W, I.useH ? I.Hsv : (const double*)nullptr, I.nv[N_DSH], rho_p, I.mv[M_RW], I.Jsv, I.nv[N_P], pf);
             ++out.nfact;
             // Growth 4 on a failed factorisation (the shift decays by 3 per iteration, so this returns to just above the
             // last value that worked).  The textbook 8-10 overshoots on the indefinite ACOPF subproblems: the extra
@@ -276,17 +312,8 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         out.rho_p = rho_p;
 
         // ---- P3 / P4: right-hand side, Newton solve ----------------------------------------------------
-        const double sigma_mu = mu_t;
-        const double tau_k = fmax(o.ipm_tau, 1.0 - mu_t);
-        for_n(T, M, [&](int i) { I.mv[M_T][i] = fma(sigma_mu, I.mv[M_YP][i], I.mv[M_TMP][i]); });
-        T.sync();
-        csr_rows(T, N, I.lgT, I.T.rb, I.T.re, I.T.col, I.Tsv, I.mv[M_T], [&](int j, double tt) {
-            const double tb = fma(sigma_mu, I.nv[N_MINV][j], I.nv[N_XFIX][j]);
-            I.nv[N_P][j] = -I.nv[N_R][j] - tt - tb;
-        });
-        T.sync();
-        pf.lap(PS_RHS);
-        chol_solve(T, C, W, I.nv[N_P], I.nv[N_XT], pf);
+        if (!R) build_rhs();
+        team_solve(T, R, C, W, I.nv[N_P], I.nv[N_XT], pf);
         // ---- P5: J dx and the step-to-boundary ratio ------------------------------------------------------
         double ratio[1] = {0.0};
         csr_rows(T, M, I.lgJ, I.J.rb, I.J.re, I.J.col, I.Jsv, I.nv[N_XT], [&](int i, double jd) {
@@ -330,6 +357,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         out.iters = it + 1;
     }
     T.sync();
+    if (R) ring_drain(*R);  // chunks requested ahead for an iteration that is not going to happen
     // Iteration cap reached while the iterate was at the acceptable level (100 x ipm_eps on every residual): returned as
     // ALMOST_LOCALLY_SOLVED, Ipopt's "solved to acceptable level".  Exits through a blow-up, a NaN or a failed
     // factorisation never promote an iterate (their acc_cnt belongs to an earlier iteration).

@@ -56,6 +56,9 @@ struct sqpqp_handle_s {
     int64_t launches = 0;
     cudaError_t async_err = cudaSuccess;  // first failure of a staged copy (upload / download); reported by finish() / the caller
     int tail_override = -1;               // development knob (sqpqp_debug_set what = 1): cap of the dense tail in columns
+    int ring_enable = 1;                  // sqpqp_debug_set what = 5: 0 keeps the slot lists (no ring programs are built); at setup
+    bool last_ring = false;
+    int ring_mode = 0;                    // what = 6: launches that stream the ring: 0 auto, 1 never, 2 whenever the programs exist
     double last_ms = 0.0;
     bool timing_pending = false;
     int num_sms = 148, coop_blocks = 0, max_dyn_smem = 0;
@@ -166,6 +169,8 @@ static void par_memcpy(void* dst, const void* src, size_t bytes) {
 // Staged host -> device copy, pipelined: the caller's buffer is copied into the pinned area in pieces and every piece
 // starts its H2D transfer as soon as it is staged, so the transfer overlaps the host copy of the next piece.
 static const size_t kStagePiece = (size_t)32 << 20;
+// one stage of the index-program ring (chol.cuh): header + 512 slots + 4 pair words per slot
+static const int kRingStageBytes = 32 + 512 * 8 + 4 * 512 * 4;
 static cudaError_t stage_h2d(sqpqp_handle h, void* ddst, size_t pin_off, const void* src, size_t bytes) {
     for (size_t o = 0; o < bytes; o += kStagePiece) {
         const size_t len = bytes - o < kStagePiece ? bytes - o : kStagePiece;
@@ -458,6 +463,8 @@ extern "C" int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value) {  /
     if (what == 2 && (value == 0 || value == 1 || value == 2 || value == 4 || value == 8)) h->ilv_G = value;
     if (what == 3 && (value == 0 || value == 256 || value == 512 || value == 1024)) h->ilv_threads = value;
     if (what == 4 && value >= 0 && value <= 2) h->ilv_occ = value;
+    if (what == 5) h->ring_enable = value != 0;
+    if (what == 6 && value >= 0 && value <= 2) h->ring_mode = value;
     return 0;
 }
 
@@ -679,7 +686,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         // one large instance runs on the cooperative grid: its dense tail lives in global memory and is factorised by
         // the whole grid in panels of 32 columns (chol.cuh: dense_factor_grid)
         const bool grid_mode = batch == 1 && (size_t)P.Ne + m > 6000;
-        auto upload_symbolic = [&](Symbolic& Sy, CholDev& C, int ncols) -> int {
+        auto upload_symbolic = [&](Symbolic& Sy, CholDev& C, int ncols, bool hasP) -> int {
             C.n = ncols; C.nnzL = Sy.nnzL; C.nlev = Sy.nlev; C.n0 = Sy.n0; C.T = Sy.T;
             C.Tpad = grid_mode ? ((Sy.T + GD_NB - 1) / GD_NB) * GD_NB : ((Sy.T + 3) & ~3);
             C.nphase = (int)Sy.fphase.size() / 4; C.n_aslot = (int)Sy.aslot_d.size(); C.nslotJ = (int)Sy.jrow.size();
@@ -696,6 +703,26 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             for (int k = 0; k < 14; ++k) {
                 int rc2 = up(*srcs[k], dsts[k]);  // cudaMalloc alignment (256 B) covers the int2 / int4 views
                 if (rc2) return rc2;
+            }
+            // ring programs of the resident CTA team (chol.cuh): chunk images for RING_S stages of kRingStageBytes; strips of
+            // up to 512 slots (one per thread of the resident launch), at most 4 pairs per lane
+            C.ring_ok = 0; C.rprog = nullptr; C.ring_nL = 0; C.ring_stage_words = 0;
+            if (!grid_mode && G == 1 && h->ring_enable) {
+                RingProg R;
+                build_ring_program(Sy, hasP, 512, 4, kRingStageBytes, RING_S, R);
+                if (R.ok) {
+                    int rc2 = up(R.words, &C.rprog);
+                    if (rc2) return rc2;
+                    C.ring_ok = 1; C.ring_nL = R.nL; C.ring_stage_words = (R.stage_words + 3) & ~3;
+                    for (int sg = 0; sg < 3; ++sg) {
+                        C.rseg_n[sg] = R.seg_count[sg];
+                        for (int q = 0; q < RING_S; ++q) {
+                            const bool on = q < R.seg_count[sg];
+                            C.rseg_off[sg][q] = on ? R.chunk_off[R.seg_first[sg] + q] : -1;
+                            C.rseg_bytes[sg][q] = on ? 4 * R.chunk_len[R.seg_first[sg] + q] : 0;
+                        }
+                    }
+                }
             }
             return 0;
         };
@@ -781,7 +808,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         DALLOC(P.wJ, B * (size_t)(P.nnzJ > 0 ? P.nnzJ : 1));
         Symbolic Sy = symbolic_analyze(n, m, hJrb.data(), hJre.data(), hJc.data(), hHrp.data(), hHc.data(), 512, tail_cap(n));
         if (Sy.ok && (int64_t)Sy.fp_ab.size() < ((int64_t)1 << 29) && Sy.nnzL < (1 << 26)) {
-            int rc2 = upload_symbolic(Sy, P.chol, n);
+            int rc2 = upload_symbolic(Sy, P.chol, n, true);
             if (rc2) return rc2;
             DALLOC(P.Lval, B * (size_t)Sy.nnzL);
             DALLOC(P.yw, B * (size_t)n);
@@ -801,7 +828,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         if (S > 0 && m > 0) {
             Symbolic Sf = symbolic_analyze(P.Ne, m, hJrb.data(), hJrb.data() + 1, hJc.data(), nullptr, nullptr, 512, tail_cap(P.Ne));
             if (Sf.ok && (int64_t)Sf.fp_ab.size() < ((int64_t)1 << 29) && Sf.nnzL < (1 << 26)) {
-                int rc2 = upload_symbolic(Sf, P.chol_fr, P.Ne);
+                int rc2 = upload_symbolic(Sf, P.chol_fr, P.Ne, false);
                 if (rc2) return rc2;
                 DALLOC(P.Lval_fr, B * (size_t)Sf.nnzL);
                 DALLOC(P.yw_fr, B * (size_t)P.Ne);
@@ -968,11 +995,11 @@ extern "C" int sqpqp_acopf_eval_update(sqpqp_handle h, const double* x, const do
 // Greedy shared-memory placement, hottest arrays first: the PCG working set (6 N-vectors +
 // 2 M-vectors), then the scaled matrix values (read 3x per PCG iteration), then the ADMM
 // iterates, then the polish scratch.  Warm-start vectors must survive the kernel and stay global.
-static void place_arrays(const Prob& P, int phase, size_t budget_bytes, bool ipm, bool vectors, Placement* pl) {
+static void place_arrays(const Prob& P, int phase, size_t budget_bytes, bool ipm, bool vectors, Placement* pl, bool ring = false) {
     const int N = (phase == SQPQP_PHASE_FR) ? P.Ne : P.n, M = P.m > 0 ? P.m : 1;
     for (int k = 0; k < N_COUNT; ++k) pl->n_off[k] = -1;
     for (int k = 0; k < M_COUNT; ++k) pl->m_off[k] = -1;
-    pl->jsv = pl->tsv = pl->hsv = pl->lval = pl->yw = pl->dtail = pl->dcol = pl->dinv = -1;
+    pl->jsv = pl->tsv = pl->hsv = pl->lval = pl->yw = pl->dtail = pl->dcol = pl->dinv = pl->ring = -1;
     pl->vec_resident = 0;
     size_t cap = budget_bytes / sizeof(double), off = 0;
     auto take = [&](int* slot, size_t len) {
@@ -988,20 +1015,31 @@ static void place_arrays(const Prob& P, int phase, size_t budget_bytes, bool ipm
         }
         take(&pl->dinv, C.n);
         take(&pl->yw, C.n);
-        if (vectors) take(&pl->lval, C.nnzL);
+        if (ring && C.ring_ok) {
+            // the ring stages, then only the part of L the ring programs touch (the tail block lives in D alone), then the
+            // vectors the sparse products gather from: with the indices streamed, those are the L2 round trips left
+            take(&pl->ring, ((size_t)RING_S * C.ring_stage_words * sizeof(int) + 7) / 8);
+            if (pl->ring >= 0) {
+                take(&pl->lval, (size_t)C.ring_nL + 1);  // + the zero entry
+                take(&pl->n_off[N_X], N);
+                take(&pl->m_off[M_T], M);
+                take(&pl->n_off[N_XT], N);
+            }
+        }
+        if (vectors && pl->lval < 0) take(&pl->lval, C.nnzL);
     }
     if (vectors) {
-        size_t before = off;
+        size_t before = (pl->ring >= 0) ? 0 : off;
         const int hotN[] = {N_P, N_KP, N_R, N_XT, N_MINV, N_DSH};
-        for (int k : hotN) take(&pl->n_off[k], N);
-        take(&pl->m_off[M_T], M);
+        for (int k : hotN) if (pl->n_off[k] < 0) take(&pl->n_off[k], N);
+        if (pl->m_off[M_T] < 0) take(&pl->m_off[M_T], M);
         take(&pl->m_off[M_RC], M);
         take(&pl->tsv, P.nnzT);
         take(&pl->jsv, P.nnzJ);
         if (phase == SQPQP_PHASE_QP || phase == SQPQP_PHASE_SOC) take(&pl->hsv, P.nnzH);
         const int warmN[] = {N_X, N_ZB, N_YB, N_RB, N_Q, N_XL, N_XU, N_HD, N_D};
         const int warmM[] = {M_ZC, M_YC, M_RL, M_RU, M_ES, M_AX};
-        for (int k : warmN) take(&pl->n_off[k], N);
+        for (int k : warmN) if (pl->n_off[k] < 0) take(&pl->n_off[k], N);
         for (int k : warmM) take(&pl->m_off[k], M);
         const int coldN[] = {N_MASK, N_XFIX, N_TMP, N_TMP2};
         const int coldM[] = {M_RW, M_BC, M_YP, M_TMP};
@@ -1061,7 +1099,11 @@ static int launch_solve(sqpqp_handle h, int phase) {
             if ((size_t)h->opts.smem_kb * 1024 < budget && vectors) budget = (size_t)h->opts.smem_kb * 1024;
         }
         Placement pl;
-        place_arrays(P, phase, budget, ipm, vectors, &pl);
+        // the resident launch (one CTA per SM) streams its index programs through the shared-memory ring when they were built
+        const bool want_ring = ipm && occ == 1 && vectors && CD.ring_ok && h->ring_mode != 1 && !(h->G > 1);
+        place_arrays(P, phase, budget, ipm, vectors, &pl, want_ring);
+        if (want_ring && (pl.ring < 0 || pl.lval < 0 || pl.dinv < 0 || pl.yw < 0 || (CD.T > 0 && pl.dtail < 0)))
+            place_arrays(P, phase, budget, ipm, vectors, &pl, false);  // does not fit next to the factor: slot lists from L2
         if (ipm && CD.T > 0 && pl.dtail < 0 && occ >= 3) {  // the tail was sized for two CTAs per SM
             occ = 2;
             if (!h->opts.threads) threads = 384;
@@ -1091,6 +1133,7 @@ static int launch_solve(sqpqp_handle h, int phase) {
         };
         if (threads > 512) threads = 512;
         if (cfg == 4 && threads > 256) threads = 256;
+        h->last_ring = pl.ring >= 0;
         const bool use_ilv = ipm && h->G > 1 && (phase == SQPQP_PHASE_FR ? h->has_ilv_fr : h->has_ilv);
         if (use_ilv) {  // G instances interleaved per CTA (ilv.cuh); flags what it cannot finish for the ADMM launch below
             CUDA_OK(launch_ilv(h, O, phase, phase == SQPQP_PHASE_FR ? h->ilv_fr : h->ilv, phase == SQPQP_PHASE_FR ? h->ilv_fr_dyn : h->ilv_dyn));
@@ -1098,7 +1141,7 @@ static int launch_solve(sqpqp_handle h, int phase) {
             h->last_kernel = "k_solve_ilv<" + std::to_string(h->G) + "," + std::to_string(h->ilv_nt) + "," + std::to_string(h->ilv_minb) + ">";
         } else if (ipm) {
             launch(1);
-            h->last_kernel = cfg == 4 ? "k_solve_cta<256,4,1>" : (cfg == 2 ? (threads <= 384 ? "k_solve_cta<384,2,1>" : "k_solve_cta<512,2,1>") : "k_solve_cta<512,1,1>");
+            h->last_kernel = cfg == 4 ? "k_solve_cta<256,4,1>" : (cfg == 2 ? (threads <= 384 ? "k_solve_cta<384,2,1>" : "k_solve_cta<512,2,1>") : (pl.ring >= 0 ? "k_solve_cta<512,1,1>+ring" : "k_solve_cta<512,1,1>"));
         } else {  // no factorisation available: every instance is "flagged" (non-zero) for the ADMM launch
             h->last_kernel = "k_solve_cta<..,2> (ADMM)";
             CUDA_OK(cudaMemsetAsync(P.fb_flag, 1, B * sizeof(int), h->stream));

@@ -22,6 +22,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 struct Symbolic {
@@ -290,6 +291,205 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
     }
     S.ok = true;
     return S;
+}
+
+// ---- ring programs: the same index work as CHUNK IMAGES for the shared-memory ring of the resident CTA team (chol.cuh) ----
+// When one CTA owns an SM and keeps the factor, the solve scratch and the gathered vectors in shared memory, the index
+// program of every barrier phase (slot -> pair list) is the only thing left to fetch.  It is static, so it is laid out here
+// as a sequence of self-contained chunk images that one thread streams into a ring of shared-memory stages with bulk
+// asynchronous copies (cp.async.bulk + mbarrier) a few chunks ahead of the consumers.  One chunk = up to `ns_max` slots of ONE
+// barrier phase:
+//   header  8 words : [0] npad (slots rounded up to 32)  [1] kmax (pairs per slot, even)  [2] 1 = assembly chunk (kinds 5 / 6:
+//                     operands in global memory, pair counts honoured), 0 = factor / sweep chunk (operands in shared memory, short
+//                     pair lists padded with the zero entry L[nL])  [3] last chunk of its segment
+//                     [4] word offset of the chunk `stages` positions later in the segment, or -1  [5] its bytes  [6] slots in use
+//   slots   npad x 2: w0 = target (16 bits) | lg << 16 | leader << 19 | has_K << 20 | pairs of this lane << 21 | kind << 28 ;  w1 = aux
+//   pairs   kmax x npad words, k-major (thread t reads word k * npad + t: conflict-free): low half = index a, high half = index b
+// kinds: 0 diagonal entry of a level (aux = column)   1 sub-diagonal entry (aux = column)   2 Schur complement of the dense
+//   tail (aux = packed position)   3 row of a triangular sweep: yw[t] = (yw[t] - sum L[a] yw[b]) dinv[t]
+//   4 tail right-hand side: yw[t] -= sum L[a] yw[b]   5 assembly into L[t]   6 assembly into the packed tail D[t]
+//   (5 / 6: a = wJ index, b = Jv index, aux = (P value index + 1) | (diagonal column + 1) << 16, 0 = none)
+// Segments: 0 = assembly + factorisation WITH the forward sweep fused in (the right-hand side is known before the
+//   factorisation in the interior-point iteration, and row j of the forward sweep needs exactly what the sub-diagonal entries
+//   of column j need -- the pivot of j and finished lower levels -- so its tasks ride in the same chunks; the tail right-hand
+//   side rides with the Schur complement), 1 = forward sweep + tail right-hand side on their own (further solves with the
+//   same factor), 2 = backward sweep.
+// All indices fit 16 bits or the program is not built (ok = false: the caller keeps the slot lists).  The tail block of L is
+// never touched in this mode (its assembled K goes straight into D), so only the first nL = Lp[n0] values (+ the zero entry)
+// must be resident.
+struct RingProg {
+    std::vector<int> words;
+    std::vector<int> chunk_off, chunk_len;  // per chunk: word offset / words of its image
+    int seg_first[3] = {0, 0, 0}, seg_count[3] = {0, 0, 0};
+    int stage_words = 0;                    // largest image
+    int nL = 0;
+    int nchunks = 0;
+    bool ok = false;
+};
+
+inline void build_ring_program(const Symbolic& S, bool has_P, int ns_max, int kcap, int stage_bytes, int stages, RingProg& out) {
+    out = RingProg();
+    const int n = S.n, n0 = S.n0;
+    out.nL = S.Lp[n0];
+    if (out.nL + 1 >= 65535 || n >= 65535 || (int)S.jrow.size() >= 65535 || S.T * (S.T + 1) / 2 + S.T >= 65535) return;
+    struct RT { int tgt, aux, hasK, kind; std::vector<std::pair<int, int>> pr; };
+    bool fail = false;
+    const int nL = out.nL;
+    auto emit = [&](std::vector<RT>& v) {
+        if (v.empty()) return;
+        const bool is_asm = v[0].kind >= 5;
+        std::stable_sort(v.begin(), v.end(), [](const RT& a, const RT& b) { return a.pr.size() > b.pr.size(); });
+        std::vector<int> lg(v.size(), 0);
+        long total = 0;
+        for (size_t t = 0; t < v.size(); ++t) {
+            const int np = (int)v[t].pr.size();
+            while (lg[t] < 5 && np > (kcap << lg[t])) ++lg[t];
+            total += 1 << lg[t];
+        }
+        while (total * 2 <= ns_max) {  // narrow phase: more lanes per task while one round of the team holds them
+            bool any = false;
+            total = 0;
+            for (size_t t = 0; t < v.size(); ++t) {
+                if (lg[t] < 5 && (int)v[t].pr.size() > (1 << lg[t])) { ++lg[t]; any = true; }
+                total += 1 << lg[t];
+            }
+            if (!any) break;
+        }
+        size_t t = 0;
+        while (t < v.size()) {
+            int ns = 0, kmax = 0;
+            size_t u = t;
+            while (u < v.size()) {
+                const int L = 1 << lg[u];
+                int kp = ((int)v[u].pr.size() + L - 1) / L;
+                kp = (kp + 1) & ~1;
+                const int ns2 = ns + L, km2 = kp > kmax ? kp : kmax, npad2 = (ns2 + 31) & ~31;
+                const long bytes = 32 + (long)npad2 * 8 + (long)km2 * npad2 * 4;
+                if (ns2 > ns_max || bytes > stage_bytes || km2 > 126) break;
+                ns = ns2; kmax = km2; ++u;
+            }
+            if (u == t) { fail = true; return; }  // one task alone does not fit a stage
+            const int npad = (ns + 31) & ~31;
+            const int off = (int)out.words.size();
+            const int len = 8 + 2 * npad + kmax * npad;
+            out.words.resize(off + len, 0);
+            int* W = &out.words[off];
+            W[0] = npad; W[1] = kmax; W[2] = is_asm ? 1 : 0; W[3] = 0; W[4] = -1; W[5] = 0; W[6] = ns; W[7] = 0;
+            int* sl = W + 8;
+            int* pw = W + 8 + 2 * npad;
+            if (!is_asm)  // short pair lists and idle slots multiply the zero entry with itself
+                for (int q = 0; q < kmax * npad; ++q) pw[q] = (int)((unsigned)nL | ((unsigned)nL << 16));
+            int s = 0;
+            for (size_t k = t; k < u; ++k) {
+                const int L = 1 << lg[k], np = (int)v[k].pr.size();
+                const unsigned padb = (v[k].kind == 3 || v[k].kind == 4) ? 0u : (unsigned)nL;  // b indexes yw in the sweeps
+                for (int lane = 0; lane < L; ++lane, ++s) {
+                    int ks = 0;
+                    for (int q = lane; q < np; q += L, ++ks) {
+                        const unsigned a = (unsigned)v[k].pr[q].first, b = (unsigned)v[k].pr[q].second;
+                        pw[ks * npad + s] = (int)(a | (b << 16));
+                    }
+                    if (!is_asm)
+                        for (int q = ks; q < kmax; ++q) pw[q * npad + s] = (int)((unsigned)nL | (padb << 16));
+                    sl[2 * s] = v[k].tgt | (lg[k] << 16) | (lane == 0 ? (1 << 19) : 0) | (v[k].hasK ? (1 << 20) : 0) | (ks << 21) | (v[k].kind << 28);
+                    sl[2 * s + 1] = v[k].aux;
+                }
+            }
+            out.chunk_off.push_back(off);
+            out.chunk_len.push_back(len);
+            if (len > out.stage_words) out.stage_words = len;
+            t = u;
+        }
+        v.clear();
+    };
+    auto close_segment = [&](int seg, int first) {
+        out.seg_first[seg] = first;
+        out.seg_count[seg] = (int)out.chunk_off.size() - first;
+        for (int c = first; c < (int)out.chunk_off.size(); ++c) {
+            int* W = &out.words[out.chunk_off[c]];
+            W[3] = (c + 1 == (int)out.chunk_off.size()) ? 1 : 0;
+            if (c + stages < (int)out.chunk_off.size()) { W[4] = out.chunk_off[c + stages]; W[5] = out.chunk_len[c + stages] * 4; }
+        }
+    };
+    auto row_task = [&](int j, int qe, int kind) {  // row j of the strictly-lower CSR up to qe
+        RT t; t.tgt = j; t.aux = 0; t.hasK = 0; t.kind = kind;
+        for (int q = S.Rp[j]; q < qe; ++q) t.pr.emplace_back(S.Rci[2 * (size_t)q], S.Rci[2 * (size_t)q + 1]);
+        return t;
+    };
+    std::vector<RT> v;
+    // ---- segment 0: assembly (entries of the sparse columns into L, entries of the tail block into D), factorisation + forward sweep ----
+    {
+        std::vector<RT> vd;
+        for (int j = 0; j < n; ++j)
+            for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
+                if (!S.hasK[e]) continue;
+                RT t;
+                t.hasK = 0;
+                const int h = has_P ? S.as_h[e] : -1, d = (e == S.Lp[j]) ? S.perm[j] : -1;
+                if (h + 1 >= 65535) { return; }
+                t.aux = (h + 1) | ((d + 1) << 16);
+                for (int q = S.as_ptr[e]; q < S.as_ptr[e + 1]; ++q) t.pr.emplace_back(S.as_ab[2 * (size_t)q], S.as_ab[2 * (size_t)q + 1]);
+                if (j < n0) { t.tgt = e; t.kind = 5; v.push_back(std::move(t)); }
+                else { const int r = S.Li[e] - n0, c = j - n0; t.tgt = r * (r + 1) / 2 + c; t.kind = 6; vd.push_back(std::move(t)); }
+            }
+        emit(v);
+        emit(vd);
+    }
+    auto fpairs = [&](int e, RT& t) {
+        for (int q = S.fp_ptr[e]; q < S.fp_ptr[e + 1]; ++q) t.pr.emplace_back(S.fp_ab[2 * (size_t)q], S.fp_ab[2 * (size_t)q + 1]);
+    };
+    for (int l = 0; l < S.nlev && !fail; ++l) {
+        for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j) { RT t; t.tgt = S.Lp[j]; t.aux = j; t.hasK = S.hasK[S.Lp[j]]; t.kind = 0; fpairs(S.Lp[j], t); v.push_back(std::move(t)); }
+        emit(v);
+        for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j) {
+            for (int e = S.Lp[j] + 1; e < S.Lp[j + 1]; ++e) { RT t; t.tgt = e; t.aux = j; t.hasK = S.hasK[e]; t.kind = 1; fpairs(e, t); v.push_back(std::move(t)); }
+            v.push_back(row_task(j, S.Rp[j + 1], 3));
+        }
+        emit(v);
+    }
+    if (S.T > 0 && !fail) {
+        for (int j = n0; j < n; ++j) {
+            for (int e = S.Lp[j]; e < S.Lp[j + 1]; ++e) {
+                RT t; const int r = S.Li[e] - n0, c = j - n0;
+                t.tgt = 0; t.aux = r * (r + 1) / 2 + c; t.hasK = 0; t.kind = 2; fpairs(e, t);
+                if (!t.pr.empty()) v.push_back(std::move(t));  // D already holds K (or 0): nothing to subtract, nothing to do
+            }
+            RT t = row_task(j, S.Rmid[j], 4);
+            if (!t.pr.empty()) v.push_back(std::move(t));
+        }
+        emit(v);
+    }
+    if (fail) return;
+    close_segment(0, 0);
+    // ---- segment 1: forward sweep (rows of L, level by level), then the right-hand side of the tail ----
+    int first = (int)out.chunk_off.size();
+    for (int l = 0; l < S.nlev && !fail; ++l) {
+        for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j) v.push_back(row_task(j, S.Rp[j + 1], 3));
+        emit(v);
+    }
+    if (S.T > 0 && !fail) {
+        for (int j = n0; j < n; ++j) {
+            RT t = row_task(j, S.Rmid[j], 4);
+            if (!t.pr.empty()) v.push_back(std::move(t));
+        }
+        emit(v);
+    }
+    if (fail) return;
+    close_segment(1, first);
+    // ---- segment 2: backward sweep (columns of L, levels descending) ----
+    first = (int)out.chunk_off.size();
+    for (int l = S.nlev - 1; l >= 0 && !fail; --l) {
+        for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j) {
+            RT t; t.tgt = j; t.aux = 0; t.hasK = 0; t.kind = 3;
+            for (int p2 = S.Lp[j] + 1; p2 < S.Lp[j + 1]; ++p2) t.pr.emplace_back(p2, S.Li[p2]);
+            v.push_back(std::move(t));
+        }
+        emit(v);
+    }
+    if (fail) return;
+    close_segment(2, first);
+    out.nchunks = (int)out.chunk_off.size();
+    out.ok = out.seg_count[0] > 0 && out.seg_count[1] > 0 && out.seg_count[2] > 0;
 }
 
 inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, SlotProg& out) {

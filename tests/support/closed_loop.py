@@ -72,8 +72,10 @@ def fr_objective(nlp, t, p, b=None):
     return float(v[nlp.num_linear_constraints:].sum())
 
 
-def check_trace(nlp, trace, oracle_every=1, marginal=1e-6, qp_tol=1e-10, verbose=False):
-    """Check every recorded subproblem; the oracle solves every `oracle_every`-th one (KKT is checked on all).
+def check_trace(nlp, trace, oracle_every=1, marginal=1e-6, qp_tol=1e-10, verbose=False, oracle_on=None, feas_checks=None):
+    """Check every recorded subproblem; the oracle solves every `oracle_every`-th one (KKT is checked on all), or exactly
+    the subproblems listed in `oracle_on`.  `feas_checks` bounds the number of HiGHS feasibility verdicts on subproblems the
+    device calls infeasible (a 2000-bus LP takes HiGHS tens of seconds; None = all).
     Returns a summary dict; raises AssertionError on a violated bar."""
     out = {"n": 0, "qp": 0, "fr": 0, "infeasible": 0, "marginal_mismatch": 0, "worst_kkt": 0.0, "oracle_solved": 0,
            "nonconvex": 0, "dev_better": 0, "dev_worse": 0, "same_step": 0, "almost": 0}
@@ -82,7 +84,7 @@ def check_trace(nlp, trace, oracle_every=1, marginal=1e-6, qp_tol=1e-10, verbose
         st = int(t["status"])
         out["n"] += 1
         P, q, A, rl, ru, xl, xu = qp_of_trace(nlp, t, b)
-        use_oracle = (k % oracle_every) == 0
+        use_oracle = (k in oracle_on) if oracle_on is not None else (k % oracle_every) == 0
         if t["fr"]:
             out["fr"] += 1
             if st in INFEAS:
@@ -108,6 +110,8 @@ def check_trace(nlp, trace, oracle_every=1, marginal=1e-6, qp_tol=1e-10, verbose
         if st in INFEAS:
             out["infeasible"] += 1
             assert not t["p"].any() and not t["lambda_qp"].any(), ("zero fill", k)  # collect_solution! :551-555
+            if feas_checks is not None and out["infeasible"] > feas_checks:
+                continue
             if qs.is_feasible(A, rl, ru, xl, xu):
                 # HiGHS did not certify infeasibility (on the 2000-bus network it can also stop without a verdict): measure
                 # how far from feasible the constraint set is.  Clearly positive -> infeasible, the device is right;

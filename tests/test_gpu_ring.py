@@ -1,0 +1,92 @@
+"""GPU parity of the resident CTA team that streams its index programs through the shared-memory ring (csrc/chol.cuh:
+ring_run_segment, cp.async.bulk + mbarrier) against the slot-list code it replaces and against the oracle's QPs.
+
+Reference: the solve at subproblem_JuMP.jl:178 (JuMP.optimize! of the QP subproblem); QP data of sqp_trust_region.jl:314-331.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "support"))
+
+import closed_loop as cl  # noqa: E402
+from sqpsolver_jl_b200 import capi  # noqa: E402
+from sqpsolver_jl_b200.host.sqp_trust_region import BatchSqpTR, Parameters  # noqa: E402
+from sqpsolver_jl_b200.nlp.acopf import AcopfPolar  # noqa: E402
+from sqpsolver_jl_b200.nlp.networks import case9, synth_net  # noqa: E402
+from sqpsolver_jl_b200.nlp.toy import ToyExample  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(HERE, "golden")
+OK = cl.OK
+
+
+def _setup(eng, nlp, batch=1):
+    eng.setup_nlp(nlp.n, nlp.m, nlp.num_linear_constraints, nlp.j_row, nlp.j_col, nlp.h_row, nlp.h_col,
+                  nlp.x_L, nlp.x_U, nlp.g_L, nlp.g_U, batch=batch)
+
+
+@pytest.mark.parametrize("name,make", [("toy_example", ToyExample), ("case9_default", lambda: AcopfPolar(case9())),
+                                       ("case118_first", lambda: AcopfPolar(synth_net(118, 186, 54, 118)))])
+def test_ring_matches_slot_lists_on_golden_subproblems(built_lib, name, make):
+    """Same subproblem, ring on / ring off: same classification, both KKT points to 1e-6, same optimal value, and nearly the
+    same number of interior-point iterations (the two programs sum the same products in a different order)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    nlp = make()
+    res = {}
+    for ring in (0, 1):
+        eng = capi.Engine(0)
+        eng.set_layout(ring=ring)
+        _setup(eng, nlp)
+        eng.set_options(warm_start=0)
+        out = []
+        for k in range(g["qp_status"].shape[0]):
+            eng.update_nlp(g["qp_dE"][k], g["qp_h_val"][k], g["qp_df"][k], g["qp_E"][k])
+            fr = bool(g["qp_fr"][k])
+            p, lam, mxL, mxU, slack, st, info = eng.solve_tr(capi.PHASE_FR if fr else capi.PHASE_QP, g["qp_x"][k], g["qp_Delta"][k])
+            out.append((p[0].copy(), lam[0].copy(), (mxL[0] + mxU[0]).copy(), int(st[0]), int(info[0]["ipm_iters"]), eng.last_solve_kernel))
+        res[ring] = out
+        eng.close()
+    assert any(o[5].endswith("+ring") for o in res[0]), [o[5] for o in res[0]][:3]
+    assert not any(o[5].endswith("+ring") for o in res[1])
+    for k, (a, b) in enumerate(zip(res[0], res[1])):
+        assert (a[3] in OK) == (b[3] in OK) and (a[3] in cl.INFEAS) == (b[3] in cl.INFEAS), (name, k, a[3], b[3])
+        if a[3] not in OK or bool(g["qp_fr"][k]):
+            continue
+        t = {"dE": g["qp_dE"][k], "h_val": g["qp_h_val"][k], "df": g["qp_df"][k], "E": g["qp_E"][k], "x": g["qp_x"][k], "Delta": g["qp_Delta"][k]}
+        P, q, A, rl, ru, xl, xu = cl.qp_of_trace(nlp, t)
+        for o in (a, b):
+            assert cl.scaled_kkt(P, q, A, rl, ru, xl, xu, o[0], o[1], o[2]) <= 1e-6, (name, k)
+        assert abs(a[4] - b[4]) <= max(3, a[4] // 4), (name, k, a[4], b[4])
+        oa = 0.5 * a[0] @ (P @ a[0]) + q @ a[0]
+        ob = 0.5 * b[0] @ (P @ b[0]) + q @ b[0]
+        if np.abs(a[0] - b[0]).max() <= 1e-6 * max(1.0, np.abs(b[0]).max()):
+            assert abs(oa - ob) <= 1e-6 * max(1.0, abs(ob))
+
+
+def test_ring_is_bit_reproducible_and_batched(built_lib):
+    """148 perturbed case118-shaped instances (one CTA per SM, ring on): two runs give identical bits; every instance is a
+    KKT point of its own QP; instance 0 equals the single-instance solve bit for bit (no cross-instance state)."""
+    B = 148
+    net = synth_net(118, 186, 54, seed=118)
+    pd, qd = net.perturbed_loads(B)
+    nlp = AcopfPolar(net, pd=pd, qd=qd)
+    runs = []
+    for _ in range(2):
+        bt = BatchSqpTR(nlp, B, Parameters(max_iter=3, init_mu=1e5))
+        bt.trace = []
+        bt.trace_instances = {0, 77, 147}
+        bt.run()
+        assert bt.optimizer.engine.last_solve_kernel.endswith("+ring"), bt.optimizer.engine.last_solve_kernel
+        runs.append((bt.x.copy(), bt.lam.copy(), [t for t in bt.trace]))
+        bt.close()
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    for b in (0, 77, 147):
+        tr = [dict(t) for t in runs[0][2] if t["b"] == b]
+        for t in tr:
+            t["b"] = None
+        s = cl.check_trace(AcopfPolar(net, pd=pd[b], qd=qd[b]), tr, oracle_every=2)
+        assert s["worst_kkt"] <= 1e-6 and s["marginal_mismatch"] <= 1, (b, s)
