@@ -138,6 +138,69 @@ def spmv_roofline(local, dev, peak, batch, reps=10):
         eng.close()
 
 
+def single_instance_2000(local, peak, max_iter=8):
+    """BASELINE configs[3]: the ~2000-bus synthetic network as ONE instance on one GPU (cooperative-grid team, k_solve_grid):
+    the QP / restoration subproblems of the first SQP iterations of the trust-region run -- the solve the reference issues
+    at subproblem_JuMP.jl:178 -- timed with CUDA events around every solve launch.  achieved = algorithmic bytes (the
+    interior-point bytes model of DESIGN.md section 5 with this network's sizes x the device-counted iterations and
+    factorisations) / kernel time.  The working set (~10 MB of values + the index programs) is L2-resident, so this is a
+    latency figure stated against the HBM roofline, as SURVEY section 8d asks; traffic = dram bytes of one launch from
+    the ncu capture recorded in profiles/r02_traffic_2000.json when it matches this kernel."""
+    from sqpsolver_jl_b200 import capi
+    from sqpsolver_jl_b200.host.sqp_trust_region import Parameters, SqpTR
+    from sqpsolver_jl_b200.nlp.acopf import AcopfPolar
+    from sqpsolver_jl_b200.nlp.networks import synth_net
+
+    nlp = AcopfPolar(synth_net(2000, 3000, 400, 2000))
+    t0 = time.perf_counter()
+    d = SqpTR(nlp, Parameters(max_iter=max_iter, init_mu=1e5), device=local)
+    setup_s = time.perf_counter() - t0
+    eng = d.batch.optimizer.engine
+    per = []
+    orig = d.batch.optimizer._solve
+
+    def hook(phase, x_k, delta, E_override=None, active=None):
+        r = orig(phase, x_k, delta, E_override, active)
+        info = d.batch.optimizer.last_info[0]
+        per.append((int(phase), float(eng.last_solve_ms), int(info["ipm_iters"]), int(info["chol_factorizations"]), int(info["moi_status"])))
+        return r
+
+    d.batch.optimizer._solve = hook
+    t0 = time.perf_counter()
+    d.run()
+    wall = time.perf_counter() - t0
+    chol = eng.chol_stats()
+    nnzJ, nnzH = int(eng.get_csr(0)[1].shape[0]), int(eng.get_csr(2)[1].shape[0])
+    kernel = eng.last_solve_kernel
+    d.close()
+    sub = [q for q in per if q[0] in (capi.PHASE_QP, capi.PHASE_FR)]
+    b_it, b_f = bytes_model_ipm(nlp.n, nlp.m, nnzJ, nnzH, max(chol["nnzL"], 1))
+    ms = float(sum(q[1] for q in sub))
+    its = int(sum(q[2] for q in sub))
+    nf = int(sum(q[3] for q in sub))
+    alg = its * b_it + nf * b_f
+    ach = alg / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic_2000.json")))
+        if tr.get("kernel") == kernel:
+            traffic = tr
+    except (OSError, ValueError):
+        pass
+    return {"workload": "ACOPF ~2000-bus synthetic network, one instance (n=%d, m=%d, nnzJ=%d, nnzH_sym=%d)" % (nlp.n, nlp.m, nnzJ, nnzH),
+            "kernel": kernel, "chol": chol, "subproblems": len(sub), "ms_per_qp": ms / max(1, len(sub)),
+            "qp_solves_per_sec": len(sub) / (ms * 1e-3) if ms > 0 else None, "ms_per_ipm_iteration": ms / max(1, its),
+            "ipm_iterations": its, "factorizations": nf, "sqp_iterations_per_sec_wall": len(sub) / wall if wall > 0 else None,
+            "setup_s_symbolic_analysis": setup_s,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+                         "bytes_per_ipm_iteration": b_it, "bytes_per_factorization": b_f,
+                         "traffic": traffic["dram_bytes"] if traffic else None,
+                         "traffic_source": {k: traffic[k] for k in ("profile", "launch", "git") if k in traffic} if traffic else None,
+                         "note": "one instance: the working set is L2-resident and the kernel is bound by grid-barrier and dependent-"
+                                 "load latency (DESIGN.md 5.3), the fraction is reported because BASELINE asks for it"},
+            "phases": [{"phase": q[0], "ms": q[1], "ipm_iters": q[2], "status": q[4]} for q in per]}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
 
@@ -374,12 +437,14 @@ def main():
         if j % R == 0:
             eng.set_options(warm_start=1)
 
+    p_zero = np.zeros_like(rec[0]["x"])
+
     def step_host(j):
         r = rec[j % R]
         if j % R == 0:
             eng.set_options(warm_start=0)
         eng.update_nlp(r["dE"], r["h_val"], r["df"], r["E"])
-        eng.merit(r["x"], np.zeros_like(r["x"]), r["E"], r["f"], r["mu"])
+        eng.merit(r["x"], p_zero, r["E"], r["f"], r["mu"])
         eng.kt_residuals(r["lam"], r["mxU"], r["mxL"])
         out = None
         if int(r["qp"].sum()):
@@ -407,6 +472,7 @@ def main():
             flush.fill_(j & 0xFF)  # L2 flush between timed steps (256 MiB > 126 MB L2)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ms0 = eng.solve_ms_total if collect_info else 0.0
             e0.record(stream)
             step_fn(warmup + j)
             e1.record(stream)
@@ -415,7 +481,7 @@ def main():
             r = rec[(warmup + j) % R]
             units += int(r["qp"].sum() + r["fr"].sum())
             if collect_info:
-                solve_ms.append(eng.last_solve_ms)
+                solve_ms.append(eng.solve_ms_total - ms0)  # every solve launch of the step (QP phase + restoration phase)
                 infos.append((eng.fetch_info(), (r["qp"] | r["fr"]).astype(bool)))
         barrier()
         return float(np.sum(times)), units, infos, solve_ms
@@ -427,6 +493,12 @@ def main():
     launches = eng.launch_count - l0
     clocks = sampler.stop()
     eng.reuse_outputs = True  # the host owns one set of result buffers and hands them to every call (no 60 MB allocation per step)
+    # ... and page-locks its persistent arrays once (sqpqp_host_register), as the reference's host would its sqp.dE / h_val / df / E /
+    # x / lambda vectors: the calls then copy straight between those arrays and the device (no staging memcpy)
+    eng.register_outputs = True
+    for r in rec:
+        eng.register_host(*[r[k] for k in ("dE", "h_val", "df", "E", "x", "Delta", "lam", "mxU", "mxL", "mu", "f", "qp", "fr")])
+    eng.register_host(p_zero)
     e_ms, e_units, _, _ = timed(step_host, args.steps, args.warmup)
 
     # max over ranks of the time, sum over ranks of the units
@@ -489,7 +561,9 @@ def main():
             "qp_solves_per_sec": units_all / (t_max * 1e-3),
             "e2e": {"value": e_units_all / (e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e_max / args.steps,
-                    "note": "host buffers in, host buffers out through sqpqp_update_nlp / merit / kt_residuals / solve_tr; result arrays owned by the caller and reused"},
+                    "note": "host buffers in, host buffers out through sqpqp_update_nlp / merit / kt_residuals / solve_tr; the caller's persistent "
+                            "arrays (inputs and results) are page-locked once with sqpqp_host_register, so every step copies them "
+                            "straight over the link (H2D and D2H inside the timed region, no staging memcpy)"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
@@ -515,6 +589,8 @@ def main():
         }
         if not args.no_spmv and world == 1:
             line["spmv"] = spmv_roofline(local, dev, peak, args.spmv_batch)
+        if not args.no_single2000 and world == 1:
+            line["single_instance_2000"] = single_instance_2000(local, peak)
         if not args.no_device_eval and world == 1:
             # the same full batched SQP solve with f, grad f, g, J and H values evaluated on the device (csrc/acopf.cuh,
             # SURVEY 8f rank 1) instead of by the host callbacks: only x and lambda go up per round

@@ -120,6 +120,15 @@ int sqpqp_set_options(sqpqp_handle h, const sqpqp_options* o);
 /* CUDA stream of the handle as a void* (cudaStream_t), for callers that time or
  * enqueue work on the same stream. */
 void* sqpqp_stream(sqpqp_handle h);
+/* Page-locks a caller-owned host buffer once (cudaHostRegister) and remembers its range.  Every later call of the NLP lane
+ * that is handed a pointer inside a registered range copies directly between that buffer and the device instead of
+ * through the library's pinned staging area (measured on the B200 box: 55 GB/s instead of ~21 GB/s).  Calls stay blocking:
+ * the buffer is free for the caller on return.  The reference's host keeps dE, h_val, df, E, x, lambda, mult_x_* as
+ * persistent vectors of the SQP object (sqp.jl:16-59) -- register those once after they are allocated.  Unregister before
+ * freeing the memory; sqpqp_destroy releases whatever is still registered.  A buffer the caller page-locked itself is
+ * accepted (only its range is recorded). */
+int sqpqp_host_register(sqpqp_handle h, void* ptr, int64_t bytes);
+int sqpqp_host_unregister(sqpqp_handle h, void* ptr);
 
 /* ---- NLP lane (fast lane B2: QpDevice <: AbstractSubOptimizer) --------------------- */
 /* Replaces the SqpTR constructor's pattern build (sqp_trust_region.jl:41-57:
@@ -261,6 +270,9 @@ int64_t sqpqp_launch_count(sqpqp_handle h);
 /* Device time (ms) of the last sqpqp_solve_tr's solve kernel, from CUDA events on
  * the handle's stream. */
 double sqpqp_last_solve_ms(sqpqp_handle h);
+/* Sum of the CUDA-event durations of every solve launch of this handle so far (one SQP step may launch the QP phase and
+ * the restoration phase; sqpqp_last_solve_ms sees only the last of them). */
+double sqpqp_solve_ms_total(sqpqp_handle h);
 /* Name and launch shape of the interior-point kernel the last solve launched (e.g. "k_solve_cta<384,2,1>",
  * "k_solve_ilv<4,512,1>", "k_solve_grid"): the launch rule lives in the library, reports read it from here. */
 const char* sqpqp_last_solve_kernel(sqpqp_handle h);

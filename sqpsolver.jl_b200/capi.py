@@ -83,6 +83,7 @@ EXPORTS = [
     "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
     "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_last_solve_kernel", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
     "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read", "sqpqp_debug_set", "sqpqp_linesearch_terms", "sqpqp_acopf_setup", "sqpqp_acopf_eval_update",
+    "sqpqp_host_register", "sqpqp_host_unregister", "sqpqp_solve_ms_total",
 ]
 
 
@@ -144,6 +145,8 @@ def lib():
     L.sqpqp_acopf_eval_update.argtypes = [vp, _dp, _dp, _ip, _dp, _dp, _dp]
     L.sqpqp_linesearch_terms.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
     L.sqpqp_debug_set.argtypes = [vp, C.c_int32, C.c_int32]
+    L.sqpqp_host_register.argtypes = [vp, vp, C.c_int64]
+    L.sqpqp_host_unregister.argtypes = [vp, vp]
     L.sqpqp_debug_read.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_int64]
     L.sqpqp_spmv.argtypes = [vp, C.c_int32, _dp, _dp]
     L.sqpqp_spmv_device.argtypes = [vp, C.c_int32, vp, vp]
@@ -158,6 +161,8 @@ def lib():
     L.sqpqp_launch_count.restype = C.c_int64
     L.sqpqp_last_solve_ms.argtypes = [vp]
     L.sqpqp_last_solve_ms.restype = C.c_double
+    L.sqpqp_solve_ms_total.argtypes = [vp]
+    L.sqpqp_solve_ms_total.restype = C.c_double
     L.sqpqp_last_solve_kernel.argtypes = [vp]
     L.sqpqp_last_solve_kernel.restype = C.c_char_p
     for name in EXPORTS:
@@ -209,6 +214,8 @@ class Engine:
         # allocating new ones -- for a batched host that owns its result buffers (bench.py's e2e leg)
         self.reuse_outputs = False
         self._out = None
+        self._registered = []  # keeps registered arrays alive
+        self.register_outputs = False  # with reuse_outputs: page-lock the persistent result arrays too
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
@@ -224,6 +231,16 @@ class Engine:
     def _ck(self, rc):
         if rc != 0:
             raise SqpQpError(f"sqpqp error {rc}: {self.L.sqpqp_last_error(self.h).decode()}")
+
+    def register_host(self, *arrays):
+        """Page-lock caller-owned numpy arrays (sqpqp_host_register): later calls that are handed these arrays copy straight
+        between them and the device.  The arrays must stay alive (and must not be reallocated) until close()."""
+        for a in arrays:
+            if a is None or a.nbytes == 0:
+                continue
+            assert a.flags["C_CONTIGUOUS"]
+            self._ck(self.L.sqpqp_host_register(self.h, C.c_void_p(a.ctypes.data), a.nbytes))
+            self._registered.append(a)
 
     def set_options(self, **kw):
         for k, v in kw.items():
@@ -296,6 +313,8 @@ class Engine:
             info = np.zeros(B, dtype=INFO_DTYPE)
             if self.reuse_outputs:
                 self._out = (p, lam, mxL, mxU, slack, status, info)
+                if self.register_outputs:
+                    self.register_host(p, lam, mxL, mxU, slack, status, info)
         self._ck(self.L.sqpqp_solve_tr(self.h, phase, _d(x_k), _d(delta), _d(E_override), _i(act), _d(p), _d(lam), _d(mxL),
                                        _d(mxU), _d(slack), _i(status), info.ctypes.data_as(C.c_void_p)))
         return p, lam, mxL, mxU, slack[:, :S], status, info
@@ -464,3 +483,8 @@ class Engine:
     @property
     def last_solve_ms(self):
         return float(self.L.sqpqp_last_solve_ms(self.h))
+
+    @property
+    def solve_ms_total(self):
+        """CUDA-event time of all solve launches of this handle so far (ms)."""
+        return float(self.L.sqpqp_solve_ms_total(self.h))

@@ -192,7 +192,7 @@ struct IpmOut {
     int iters, nfact;
     double rp, rd, rho_p;
 };
-template <class Team>
+template <bool RING, class Team>
 __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, Ring* R, const sqpqp_options& o,
                           double c, int phase, const double* xk_scaled_start);
 __device__ __forceinline__ void ring_init(Ring& R, const CholDev& C, const CholWork& W, int stage0_dbl, unsigned long long* bars);
@@ -214,7 +214,9 @@ __device__ __forceinline__ void ring_init(Ring& R, const CholDev& C, const CholW
     (void)tmpN; (void)tmpN2; (void)xw; (void)ybw; (void)rl; (void)ru; (void)Es; (void)zc; (void)yc; (void)rc; (void)tmpM; \
     (void)Ax; (void)ycw;
 
-template <int MODE, class Team>
+// RING: the launch may stream its index programs through the shared-memory ring (one resident CTA per SM only: the code is
+// compiled out of the other variants, where its registers would turn into spills)
+template <int MODE, class Team, bool RING = false>
 __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, int inst, int phase,
                                const Placement* pl, double* dsm, unsigned long long* rbar = nullptr) {
     if constexpr (MODE == 2) {
@@ -400,12 +402,14 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
         Ring R;
         R.on = false;
         W.oL = W.oyw = W.odinv = W.oD = -1;
-        if (pl && rbar && pl->ring >= 0 && CD.ring_ok) {  // ring mode: L, yw, dinv (and the tail) are in shared memory (launch_solve)
-            W.oL = pl->lval; W.oyw = pl->yw; W.odinv = pl->dinv; W.oD = pl->dtail >= 0 ? pl->dtail : 0;
-            ring_init(R, CD, W, pl->ring, rbar);
+        if constexpr (RING) {
+            if (pl && rbar && pl->ring >= 0 && CD.ring_ok) {  // ring mode: L, yw, dinv (and the tail) are in shared memory (launch_solve)
+                W.oL = pl->lval; W.oyw = pl->yw; W.odinv = pl->dinv; W.oD = pl->dtail >= 0 ? pl->dtail : 0;
+                ring_init(R, CD, W, pl->ring, rbar);
+            }
         }
         pfo.lap(PS_PROLOGUE);
-        IpmOut io = ipm_run(T, I, CD, W, R.on ? &R : (Ring*)nullptr, o, c, phase, start);
+        IpmOut io = ipm_run<RING>(T, I, CD, W, (RING && R.on) ? &R : (Ring*)nullptr, o, c, phase, start);
         pfo.start();
         ipm_iters = io.iters;
         nfact = io.nfact;
@@ -831,7 +835,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(const __grid_constant_
     for (int inst = blockIdx.x; inst < P.batch; inst += gridDim.x) {
         if (P.active && !P.active[inst]) continue;
         CtaTeam T(sh);
-        solve_instance<MODE>(T, P, O.o, inst, phase, &pl, dsm, MODE == 2 ? (unsigned long long*)nullptr : rbar);
+        solve_instance<MODE, CtaTeam, (MINB == 1 && MODE == 1)>(T, P, O.o, inst, phase, &pl, dsm, rbar);
         __syncthreads();
     }
 }

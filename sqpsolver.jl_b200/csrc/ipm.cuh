@@ -57,9 +57,10 @@ __device__ __forceinline__ void team_solve(CtaTeam& T, Ring* R, const CholDev& C
     else chol_solve(T, C, W, b, x, pf);
 }
 
-template <class Team>
-__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, Ring* R, const sqpqp_options& o,
+template <bool RING, class Team>
+__device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, Ring* Rin, const sqpqp_options& o,
                           double c, int phase, const double* xk_scaled_start) {
+    Ring* const R = RING ? Rin : (Ring*)nullptr;  // a compile-time null outside the resident launch: the ring code folds away
     const int N = I.N, M = I.M;
     // Work vectors are slots of the ADMM workspace (the two methods never run concurrently), addressed through
     // I.nv / I.mv at the point of use (kernel-parameter bank, no per-thread pointer table):

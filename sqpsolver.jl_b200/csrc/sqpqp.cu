@@ -33,7 +33,10 @@ struct Pending {
 struct sqpqp_handle_s {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // pair in use (one of tev[], or the SpMV pair)
+    cudaEvent_t tev[4][2] = {};                 // ring of event pairs of the solve launches
+    cudaEvent_t sev[2] = {};                    // pair of the SpMV timing
+    int tp_head = 0, tp_n = 0;
     std::string err;
     sqpqp_options opts;
     bool setup_done = false, updated = false;
@@ -58,9 +61,14 @@ struct sqpqp_handle_s {
     int tail_override = -1;               // development knob (sqpqp_debug_set what = 1): cap of the dense tail in columns
     int ring_enable = 1;                  // sqpqp_debug_set what = 5: 0 keeps the slot lists (no ring programs are built); at setup
     bool last_ring = false;
+    // caller buffers page-locked with sqpqp_host_register: copied to / from the device directly, without the pinned staging hop
+    std::vector<std::pair<const char*, size_t>> host_pinned;
+    std::vector<const char*> host_owned_reg;  // the subset this handle page-locked itself (and must unlock)
     int ring_mode = 0;                    // what = 6: launches that stream the ring: 0 auto, 1 never, 2 whenever the programs exist
     double last_ms = 0.0;
     bool timing_pending = false;
+    bool timing_is_solve = false;         // the pending event pair brackets a solve launch (else an SpMV)
+    double solve_ms_total = 0.0;          // CUDA-event time of every solve launch so far (sqpqp_solve_ms_total)
     int num_sms = 148, coop_blocks = 0, max_dyn_smem = 0;
     int chol_nnzL = 0, chol_nlev = 0, chol_tail = 0, chol_nlev_total = 0;
     int cta4_smem = 48 * 1024;  // dynamic shared memory of one CTA when four share an SM
@@ -168,10 +176,20 @@ static void par_memcpy(void* dst, const void* src, size_t bytes) {
 
 // Staged host -> device copy, pipelined: the caller's buffer is copied into the pinned area in pieces and every piece
 // starts its H2D transfer as soon as it is staged, so the transfer overlaps the host copy of the next piece.
+static bool is_registered(sqpqp_handle h, const void* p, size_t bytes) {
+    const char* c = (const char*)p;
+    for (auto& r : h->host_pinned)
+        if (c >= r.first && c + bytes <= r.first + r.second) return true;
+    return false;
+}
 static const size_t kStagePiece = (size_t)32 << 20;
 // one stage of the index-program ring (chol.cuh): header + 512 slots + 4 pair words per slot
+static const int kTimingRing = 4;
 static const int kRingStageBytes = 32 + 512 * 8 + 4 * 512 * 4;
 static cudaError_t stage_h2d(sqpqp_handle h, void* ddst, size_t pin_off, const void* src, size_t bytes) {
+    // a registered (page-locked) caller buffer goes over the link as it is: the staging memcpy tops out near 21 GB/s on the
+    // B200 box, the link itself gives 55 GB/s (tools/gpu_pcie.py)
+    if (is_registered(h, src, bytes)) return cudaMemcpyAsync(ddst, src, bytes, cudaMemcpyHostToDevice, h->stream);
     for (size_t o = 0; o < bytes; o += kStagePiece) {
         const size_t len = bytes - o < kStagePiece ? bytes - o : kStagePiece;
         par_memcpy(h->pin + pin_off + o, (const char*)src + o, len);
@@ -204,6 +222,11 @@ static void download(sqpqp_handle h, const T* dsrc, T* user, size_t count) {
     size_t off = h->stage_off;
     if (off + bytes > h->stage_cap) {
         if (h->async_err == cudaSuccess) h->async_err = cudaErrorInvalidValue;
+        return;
+    }
+    if (is_registered(h, user, bytes)) {  // straight into the caller's page-locked buffer; finish() waits for the stream
+        cudaError_t ce = cudaMemcpyAsync(user, dsrc, bytes, cudaMemcpyDeviceToHost, h->stream);
+        if (ce != cudaSuccess && h->async_err == cudaSuccess) h->async_err = ce;
         return;
     }
     h->stage_off = align256(off + bytes);
@@ -322,6 +345,12 @@ extern "C" void sqpqp_default_options(sqpqp_options* o) {
     o->ipm_rho0 = 1e-8; o->ipm_tau = 0.995; o->ipm_mu0 = 1.0; o->ipm_mu_min = 1e-14; o->ipm_kappa_eps = 10.0; o->ipm_refine = 0; o->verbose = 0;
 }
 
+static bool create_timing_events(sqpqp_handle h) {
+    for (auto& pr : h->tev) for (auto& e : pr) if (cudaEventCreate(&e) != cudaSuccess) return false;
+    for (auto& e : h->sev) if (cudaEventCreate(&e) != cudaSuccess) return false;
+    h->ev0 = h->tev[0][0]; h->ev1 = h->tev[0][1];
+    return true;
+}
 extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
     if (!out) return SQPQP_E_BADARG;
     *out = nullptr;
@@ -334,7 +363,7 @@ extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
     sqpqp_default_options(&h->opts);
     DeviceGuard g(device);
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        !create_timing_events(h)) {
         delete h;
         return SQPQP_E_CUDA;
     }
@@ -375,25 +404,79 @@ extern "C" int sqpqp_destroy(sqpqp_handle h) {
     if (!h) return SQPQP_E_BADARG;
     DeviceGuard g(h->device);
     free_problem(h);
+    for (auto q : h->host_owned_reg) cudaHostUnregister((void*)q);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->dstage) cudaFree(h->dstage);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (auto& pr : h->tev) for (auto e : pr) if (e) cudaEventDestroy(e);
+    for (auto e : h->sev) if (e) cudaEventDestroy(e);
     for (auto e : h->evpool) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
 }
 
+// Page-lock a caller-owned host buffer (cudaHostRegister) and remember its range: every later call that is handed a pointer
+// inside it copies directly between that buffer and the device.  The calls stay blocking, so the buffer is free on return
+// exactly as before.  A host that owns persistent arrays (the reference's sqp.dE / h_val / df / E / x / lambda ...,
+// sqp.jl:16-59) registers them once after allocation.
+extern "C" int sqpqp_host_register(sqpqp_handle h, void* ptr, int64_t bytes) {
+    if (!h || !ptr || bytes <= 0) return SQPQP_E_BADARG;
+    DeviceGuard g(h->device);
+    if (is_registered(h, ptr, (size_t)bytes)) return 0;
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); e = cudaSuccess; }  // by the caller (e.g. a pinned allocator)
+    else if (e != cudaSuccess) return fail_cuda(h, e, "cudaHostRegister", __LINE__);
+    else h->host_owned_reg.push_back((const char*)ptr);
+    h->host_pinned.emplace_back((const char*)ptr, (size_t)bytes);
+    return 0;
+}
+extern "C" int sqpqp_host_unregister(sqpqp_handle h, void* ptr) {
+    if (!h || !ptr) return SQPQP_E_BADARG;
+    DeviceGuard g(h->device);
+    for (size_t k = 0; k < h->host_pinned.size(); ++k)
+        if (h->host_pinned[k].first == (const char*)ptr) {
+            cudaStreamSynchronize(h->stream);
+            for (size_t q = 0; q < h->host_owned_reg.size(); ++q)
+                if (h->host_owned_reg[q] == (const char*)ptr) {
+                    cudaHostUnregister(ptr);
+                    h->host_owned_reg.erase(h->host_owned_reg.begin() + q);
+                    break;
+                }
+            h->host_pinned.erase(h->host_pinned.begin() + k);
+            return 0;
+        }
+    return fail(h, SQPQP_E_BADARG, "buffer was not registered");
+}
+
 extern "C" const char* sqpqp_last_error(sqpqp_handle h) { return h ? h->err.c_str() : "null handle"; }
 extern "C" void* sqpqp_stream(sqpqp_handle h) { return h ? (void*)h->stream : nullptr; }
 extern "C" int64_t sqpqp_launch_count(sqpqp_handle h) { return h ? h->launches : 0; }
+// Sum of the CUDA-event durations of all solve launches of this handle so far (a step of the batched SQP may launch the QP
+// phase and the restoration phase: sqpqp_last_solve_ms only sees the last one).
+extern "C" double sqpqp_last_solve_ms(sqpqp_handle h);
+extern "C" double sqpqp_solve_ms_total(sqpqp_handle h) {
+    if (!h) return 0.0;
+    sqpqp_last_solve_ms(h);
+    return h->solve_ms_total;
+}
 extern "C" double sqpqp_last_solve_ms(sqpqp_handle h) {
     if (!h) return 0.0;
     if (h->timing_pending) {
         DeviceGuard g(h->device);
         float ms = 0.f;
-        if (cudaEventSynchronize(h->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
+        if (h->timing_is_solve) {  // every pending pair of the ring, oldest first
+            while (h->tp_n > 0) {
+                cudaEvent_t a = h->tev[h->tp_head][0], b = h->tev[h->tp_head][1];
+                if (cudaEventSynchronize(b) == cudaSuccess && cudaEventElapsedTime(&ms, a, b) == cudaSuccess) {
+                    h->last_ms = ms;
+                    h->solve_ms_total += ms;
+                }
+                h->tp_head = (h->tp_head + 1) % kTimingRing;
+                h->tp_n--;
+            }
+        } else if (cudaEventSynchronize(h->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) {
+            h->last_ms = ms;
+        }
         h->timing_pending = false;
     }
     return h->last_ms;
@@ -1068,6 +1151,14 @@ static int launch_solve(sqpqp_handle h, int phase) {
     // a dense tail laid out for the CTA team (panels of 4, shared memory) cannot be run by the grid team and vice versa
     if (team == 2 && ((phase == SQPQP_PHASE_FR ? P.chol_fr.T : P.chol.T) > 0) && !(phase == SQPQP_PHASE_FR ? P.Dtail_fr : P.Dtail)) team = 1;
     if (team == 1 && ((phase == SQPQP_PHASE_FR ? P.chol_fr.T : P.chol.T) > 0) && (phase == SQPQP_PHASE_FR ? P.Dtail_fr : P.Dtail)) team = 2;
+    // event pair of this launch: a small ring, so that back-to-back launches (QP phase, then restoration phase) need no host
+    // synchronisation between them; a slot is only waited for when the ring wraps around to it
+    if (h->timing_pending && h->timing_is_solve && h->tp_n == kTimingRing) sqpqp_last_solve_ms(h);
+    if (!h->timing_is_solve && h->timing_pending) sqpqp_last_solve_ms(h);
+    {
+        const int slot = (h->tp_head + h->tp_n) % kTimingRing;
+        h->ev0 = h->tev[slot][0]; h->ev1 = h->tev[slot][1];
+    }
     CUDA_OK(cudaEventRecord(h->ev0, h->stream));
     if (team == 2) {
         void* args[] = {(void*)&P, (void*)&O, (void*)&phase};
@@ -1152,6 +1243,8 @@ static int launch_solve(sqpqp_handle h, int phase) {
     h->launches++;
     CUDA_OK(cudaEventRecord(h->ev1, h->stream));
     h->timing_pending = true;
+    h->timing_is_solve = true;
+    h->tp_n++;
     return 0;
 }
 
@@ -1370,11 +1463,14 @@ extern "C" int sqpqp_spmv_device(sqpqp_handle h, int32_t which, const double* x_
     if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
     if (which < 0 || which > 2 || !x_dev || !y_dev) return fail(h, SQPQP_E_BADARG, "bad selector or null pointer");
     DeviceGuard g(h->device);
+    if (h->timing_pending) sqpqp_last_solve_ms(h);
+    h->ev0 = h->sev[0]; h->ev1 = h->sev[1];
     CUDA_OK(cudaEventRecord(h->ev0, h->stream));
     int rc = launch_spmv(h, which, x_dev, y_dev);
     if (rc) return rc;
     CUDA_OK(cudaEventRecord(h->ev1, h->stream));
     h->timing_pending = true;
+    h->timing_is_solve = false;
     return 0;
 }
 

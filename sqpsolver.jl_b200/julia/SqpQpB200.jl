@@ -72,6 +72,10 @@ mutable struct QpDevice
 end
 
 "eval_functions!/eval_Jacobian! scatter (sqp.jl:86-117) + QpData refresh (sqp.jl:66-79)"
+# Page-lock the host's persistent vectors once (sqp.dE, sqp.h_val, sqp.df, sqp.E, sqp.x, sqp.lambda, ...: sqp.jl:16-59): every
+# later call copies them straight over the link instead of through the library's staging area.
+register!(qp::QpDevice, v::Vector) = check(qp.h, ccall((:sqpqp_host_register, libsqpqp), Cint,
+    (Ptr{Cvoid}, Ptr{Cvoid}, Int64), qp.h, pointer(v), sizeof(v)))
 update!(qp::QpDevice, dE, h_val, df, E) = check(qp.h, ccall((:sqpqp_update_nlp, libsqpqp), Cint,
     (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), qp.h, dE, h_val, df, E))
 

@@ -101,7 +101,10 @@ def check_trace(nlp, trace, oracle_every=1, marginal=1e-6, qp_tol=1e-10, verbose
                 ro = ora.sub_optimize_FR(t["x"], t["Delta"])
                 assert ro[-1] in qs.OK_STATUSES, ("oracle FR", k, ro[-1])
                 o_obj, d_obj = fr_objective(nlp, t, ro[0], b), fr_objective(nlp, t, t["p"], b)
-                assert abs(d_obj - o_obj) <= 1e-6 * max(1.0, abs(o_obj)), ("FR optimum", k, d_obj, o_obj)
+                # 1e-6 for a solve that met the full tolerance; an ALMOST_LOCALLY_SOLVED one (Ipopt's "acceptable level":
+                # residuals at 1e-6, the status the reference accepts at sqp_trust_region.jl:144) is held to 1e-5
+                ftol = 1e-5 if st == capi.MOI_ALMOST_LOCALLY_SOLVED else 1e-6
+                assert abs(d_obj - o_obj) <= ftol * max(1.0, abs(o_obj)), ("FR optimum", k, d_obj, o_obj, st)
                 out["oracle_solved"] += 1
             # the step must respect box and linear rows
             assert (t["p"] >= xl - 1e-7).all() and (t["p"] <= xu + 1e-7).all(), ("FR box", k)

@@ -28,11 +28,44 @@ class DeviceSub:
         self.engine = engine
         self.data = None
         self.n_solves = 0
+        self.is_setup = False
+
+    def ensure_setup(self):
+        if not self.is_setup:
+            pr = self.driver.problem
+            self.engine.setup_nlp(pr.n, pr.m, pr.num_linear_constraints, pr.j_row, pr.j_col, pr.h_row, pr.h_col, pr.x_L, pr.x_U,
+                                  pr.g_L, pr.g_U)
+            self.is_setup = True
+
+    def sub_optimize_lp(self):
+        """sub_optimize_lp! (sqp_trust_region.jl:264-304) of the oracle driver with the device's start-point projection
+        (phase 3) in place of the CPU oracle's: both drivers of a parity test then start from the same point."""
+        d = self.driver
+        pr = d.problem
+        d.f = float(pr.eval_f(d.x))
+        pr.eval_grad_f(d.x, d.df)
+        d.eval_Jacobian()
+        self.ensure_setup()
+        E = np.zeros(pr.m)
+        pr.eval_g(d.x, E)
+        self.engine.update_nlp(d.dE, d.h_val, d.df, E)
+        xs, lam, mxL, mxU, _, st, _ = self.engine.solve_tr(capi.PHASE_LP, d.x, np.inf)
+        self.n_solves += 1
+        d.n_qp += 1
+        ok = int(st[0]) in (1, 4, 7, 10)
+        lam = lam[0].copy()
+        lam[pr.num_linear_constraints:] = 0.0
+        outs = [xs[0].copy(), lam, mxU[0].copy(), mxL[0].copy()]
+        for v in outs:
+            if not ok:
+                v[:] = 0.0
+            v[np.abs(v) < 1e-10] = 0.0  # dropzeros! (utils.jl:16-22)
+        d.x, d.lam, d.mult_x_U, d.mult_x_L = outs
+        d.sub_status = NAME.get(int(st[0]), "OTHER_ERROR")
 
     def create_model(self, delta):
         pr = self.driver.problem
-        self.engine.setup_nlp(pr.n, pr.m, pr.num_linear_constraints, pr.j_row, pr.j_col, pr.h_row, pr.h_col, pr.x_L, pr.x_U,
-                              pr.g_L, pr.g_U)
+        self.ensure_setup()
         ml, m = pr.num_linear_constraints, pr.m
         self.slack_rows = []
         for i in range(ml, m):
@@ -59,7 +92,9 @@ class DeviceSub:
 
 def attach(driver, engine):
     """Make `driver` (an oracle SqpTROracle / SqpLSOracle) solve its subproblems on the device."""
-    driver.sub_factory = lambda data: _with_data(DeviceSub(driver, engine), data)
+    sub = DeviceSub(driver, engine)
+    driver.sub_factory = lambda data: _with_data(sub, data)
+    driver.sub_optimize_lp = sub.sub_optimize_lp  # the start-point projection goes through the device as well
     return driver
 
 

@@ -167,7 +167,9 @@ def test_generic_lane_with_the_jump_model_of_the_reference(built_lib, make, kw):
         # the multiplier face, the Hessian of the next iteration is evaluated with them (sqp.jl:93) and the runs separate
         # from iteration 2 on -- both reach the same optimum (asserted above)
         r = replay[0]
-        assert r.n_solves == gen.n_qp
+        # every QP / restoration subproblem went through the generic lane (n_qp also counts the start-point projection, which
+        # the oracle driver solves on the CPU when the start violates a linear row or a bound: subproblem_JuMP.jl:185-244)
+        assert len(replay) == 1 and r.n_solves in (gen.n_qp, gen.n_qp - 1)
         # the device structure is rebuilt only when the pattern of the model changes (QP <-> restoration LP objective)
         assert r.n_setups <= 2 * sum(1 for a, b in zip(log_g, log_g[1:]) if a["fr"] != b["fr"]) + 2
     finally:

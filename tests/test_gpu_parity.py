@@ -597,6 +597,34 @@ def test_caller_owned_result_buffers(engine):
     engine.reuse_outputs = False
 
 
+def test_registered_host_buffers_give_identical_results(engine):
+    """sqpqp_host_register: page-locked caller buffers are copied directly (no staging hop); same bits either way, and a
+    buffer can be unregistered again."""
+    g = np.load(os.path.join(GOLD, "case9_mu1e4.npz"))
+    nlp = AcopfPolar(case9())
+    _setup(engine, nlp)
+    engine.set_options(warm_start=0)
+    ins = [np.ascontiguousarray(g[k][3], dtype=np.float64).reshape(1, -1).copy() for k in ("qp_dE", "qp_h_val", "qp_df", "qp_E", "qp_x")]
+    engine.update_nlp(*ins[:4])
+    plain = [v.copy() for v in engine.solve_tr(capi.PHASE_QP, ins[4], g["qp_Delta"][3])[:6]]
+    engine.register_host(*ins)
+    engine.reuse_outputs = True
+    engine.register_outputs = True
+    engine.update_nlp(*ins[:4])
+    reg = engine.solve_tr(capi.PHASE_QP, ins[4], g["qp_Delta"][3])
+    assert all(np.array_equal(a, b) for a, b in zip(plain, reg[:6]))
+    m1 = engine.merit(ins[4], np.zeros_like(ins[4]), ins[3], np.zeros(1), np.ones(1))
+    rc = engine.L.sqpqp_host_unregister(engine.h, ins[0].ctypes.data)
+    assert rc == 0
+    assert engine.L.sqpqp_host_unregister(engine.h, ins[0].ctypes.data) != 0  # not registered any more
+    engine.update_nlp(*ins[:4])  # goes through the staging area again
+    again = engine.solve_tr(capi.PHASE_QP, ins[4], g["qp_Delta"][3])
+    assert all(np.array_equal(a, b) for a, b in zip(plain, again[:6]))
+    m2 = engine.merit(ins[4], np.zeros_like(ins[4]), ins[3], np.zeros(1), np.ones(1))
+    assert all(np.array_equal(a, b) for a, b in zip(m1, m2))
+    engine.reuse_outputs = False
+
+
 def test_error_paths(engine):
     import ctypes as C
     rc = engine.L.sqpqp_update_nlp(engine.h, None, None, None, None)  # update before setup
