@@ -73,13 +73,13 @@ __device__ __forceinline__ double column_dot(const double* __restrict__ V, const
 // Two pair lists walked together, two pairs of each per trip: eight independent gathers in flight.  A thread that owns
 // two slots of a phase pays the index -> value round trips once for both.
 __device__ __forceinline__ void gather_dot2(const int2* __restrict__ ab, int qa, const int ea, const int sa, int qb, const int eb,
-                                            const int sb, const double* A, const double* B, double& ra, double& rb) {
+                                            const int sb, const double* A, const double* Ba, const double* Bb, double& ra, double& rb) {
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
     while (qa < ea || qb < eb) {
         const bool a_1 = qa < ea, a_2 = qa + sa < ea, b_1 = qb < eb, b_2 = qb + sb < eb;
         const int2 pa1 = ab[a_1 ? qa : 0], pa2 = ab[a_2 ? qa + sa : 0], pb1 = ab[b_1 ? qb : 0], pb2 = ab[b_2 ? qb + sb : 0];
-        const double xa1 = A[pa1.x], ya1 = B[pa1.y], xa2 = A[pa2.x], ya2 = B[pa2.y];
-        const double xb1 = A[pb1.x], yb1 = B[pb1.y], xb2 = A[pb2.x], yb2 = B[pb2.y];
+        const double xa1 = A[pa1.x], ya1 = Ba[pa1.y], xa2 = A[pa2.x], ya2 = Ba[pa2.y];
+        const double xb1 = A[pb1.x], yb1 = Bb[pb1.y], xb2 = A[pb2.x], yb2 = Bb[pb2.y];
         if (a_1) a0 = fma(xa1, ya1, a0);
         if (a_2) a1 = fma(xa2, ya2, a1);
         if (b_1) b0 = fma(xb1, yb1, b0);
@@ -327,7 +327,7 @@ __device__ void chol_assemble(Team& T, const CholDev& C, const CholWork& W, cons
             if (d >= 0) vB += dg[d] + shift;
         }
         double accA, accB;
-        gather_dot2(C.as_ab, onA ? slA.y : 0, onA ? slA.z : 0, LnA, onB ? slB.y : 0, onB ? slB.z : 0, LnB, wJ, Jv, accA, accB);
+        gather_dot2(C.as_ab, onA ? slA.y : 0, onA ? slA.z : 0, LnA, onB ? slB.y : 0, onB ? slB.z : 0, LnB, wJ, Jv, Jv, accA, accB);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double tA = __shfl_xor_sync(0xffffffffu, accA, o), tB = __shfl_xor_sync(0xffffffffu, accB, o);
@@ -636,10 +636,15 @@ __device__ __forceinline__ void team_dense_solve(GridTeam&, const CholDev& C, co
 // diagonal entries, then the sub-diagonal entries; then the Schur complement of the dense tail).  A
 // thread executes one SLOT per round: one lane's share of a task, the lane count chosen per task on
 // the host from its pair count.  Returns false (uniformly) if a pivot was not positive.
+// With a fused program (C.fused_fwd) and a right-hand side b, the forward sweep of the solve K x = b rides in the same
+// phases (sweep slots: bit 31, pairs (L value, row of yw)); chol_solve is then called with skip_fwd.
 template <class Team>
-__device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& pf) {
+__device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& pf, const double* b = nullptr) {
     double* L = W.L;
+    double* yw = W.yw;
     double bad[1] = {0.0};
+    if (C.fused_fwd && b)  // first read of yw is in the second phase, behind the barrier of the first
+        for (int k = T.tid(); k < C.n; k += T.size()) yw[k] = b[C.perm[k]];
     int4 ph = C.fphase[0];
     for (int p = 0; p < C.nphase; ++p) {
         const int4 nxt = C.fphase[p + 1];  // (padded by one entry) off the critical path of the next phase
@@ -651,10 +656,13 @@ __device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& 
             const int eA = slA.x & 0x3ffffff, eB = slB.x & 0x3ffffff;
             const int LnA = 1 << ((slA.x >> 26) & 7), LnB = 1 << ((slB.x >> 26) & 7);
             const bool ldA = onA && ((slA.x >> 29) & 1), ldB = onB && ((slB.x >> 29) & 1);
-            const double kA = (ldA && (slA.x >> 30)) ? L[eA] : 0.0, kB = (ldB && (slB.x >> 30)) ? L[eB] : 0.0;
+            const bool swA = slA.x < 0, swB = slB.x < 0;  // forward-sweep slot
+            const double kA = !ldA ? 0.0 : (swA ? yw[eA] : (((slA.x >> 30) & 1) ? L[eA] : 0.0));
+            const double kB = !ldB ? 0.0 : (swB ? yw[eB] : (((slB.x >> 30) & 1) ? L[eB] : 0.0));
             const double dA = (ldA && kind == 1) ? W.dinv[slA.w] : 0.0, dB = (ldB && kind == 1) ? W.dinv[slB.w] : 0.0;
             double accA, accB;
-            gather_dot2(C.fp_ab, onA ? slA.y : 0, onA ? slA.z : 0, LnA, onB ? slB.y : 0, onB ? slB.z : 0, LnB, L, L, accA, accB);
+            gather_dot2(C.fp_ab, onA ? slA.y : 0, onA ? slA.z : 0, LnA, onB ? slB.y : 0, onB ? slB.z : 0, LnB, L, swA ? yw : L,
+                        swB ? yw : L, accA, accB);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {  // lane groups of mixed (power of two, aligned) sizes share the butterfly
                 const double tA = __shfl_xor_sync(0xffffffffu, accA, o), tB = __shfl_xor_sync(0xffffffffu, accB, o);
@@ -663,7 +671,9 @@ __device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& 
             }
             if (ldA) {
                 double v = kA - accA;
-                if (kind == 0) {
+                if (swA) {
+                    yw[eA] = kind == 1 ? v * dA : v;  // row of a sparse level / right-hand side of the tail
+                } else if (kind == 0) {
                     if (!(v > 0.0)) { bad[0] = 1.0; v = 1.0; }
                     const double inv = rsqrt(v);
                     L[eA] = v * inv;
@@ -676,7 +686,9 @@ __device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& 
             }
             if (ldB) {
                 double v = kB - accB;
-                if (kind == 0) {
+                if (swB) {
+                    yw[eB] = kind == 1 ? v * dB : v;
+                } else if (kind == 0) {
                     if (!(v > 0.0)) { bad[0] = 1.0; v = 1.0; }
                     const double inv = rsqrt(v);
                     L[eB] = v * inv;
@@ -701,14 +713,17 @@ __device__ bool chol_factor(Team& T, const CholDev& C, const CholWork& W, Prof& 
 }
 
 // x = K^{-1} b   (b, x in original order; x may alias b)
+// skip_fwd: the forward sweep and the tail right-hand side were done by chol_factor (fused program): yw already holds them
 template <class Team>
-__device__ void chol_solve(Team& T, const CholDev& C, const CholWork& W, const double* b, double* x, Prof& pf) {
+__device__ void chol_solve(Team& T, const CholDev& C, const CholWork& W, const double* b, double* x, Prof& pf, const bool skip_fwd = false) {
     const double* L = W.L;
     double* yw = W.yw;
     const double* dinv = W.dinv;
+    if (!skip_fwd) {
     for (int k = T.tid(); k < C.n; k += T.size()) yw[k] = b[C.perm[k]];
     T.sync();
-    for (int l = 0; l < C.nlev; ++l) {  // forward: rows of L
+    }
+    for (int l = 0; l < (skip_fwd ? 0 : C.nlev); ++l) {  // forward: rows of L
         const int c0 = C.lev_ptr[l], cnt = C.lev_ptr[l + 1] - c0, lg = level_lg(T, cnt), Ln = 1 << lg;
         const int lane = T.tid() & (Ln - 1), sub = T.tid() >> lg, nsub = T.size() >> lg;
         for (int t0 = 0; t0 < cnt; t0 += nsub) {
@@ -727,7 +742,7 @@ __device__ void chol_solve(Team& T, const CholDev& C, const CholWork& W, const d
         // tail right-hand side: b_j - sum_{k < n0} L_jk y_k, then the dense solves (one warp)
         const int lg = level_lg(T, C.T), Ln = 1 << lg;
         const int lane = T.tid() & (Ln - 1), sub = T.tid() >> lg, nsub = T.size() >> lg;
-        for (int t0 = 0; t0 < C.T; t0 += nsub) {
+        for (int t0 = 0; t0 < (skip_fwd ? 0 : C.T); t0 += nsub) {
             const int t = t0 + sub;
             const bool on = t < C.T;
             const int j = C.n0 + (on ? t : 0);

@@ -46,6 +46,7 @@ struct CholDev {
     int n, nnzL, nlev, n0, T;
     int Tpad;               // T rounded up to the panel width of the dense code (4: CTA team, 32: grid team); padding rows are identity
     int nphase, n_aslot, nslotJ;
+    int fused_fwd;          // the factor program carries the forward sweep of the Newton solve (symbolic.hpp: fuse_fwd)
     const int *perm;
     const int *Lp, *Li;
     const int *Rp, *Rmid;

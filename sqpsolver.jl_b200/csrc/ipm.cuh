@@ -37,24 +37,24 @@ __device__ __forceinline__ double step_ratio(double v, double dv) { return dv < 
 // the right-hand side b is then needed BEFORE the factorisation, because its forward sweep rides in the factor chunks.
 template <class Team>
 __device__ __forceinline__ bool team_assemble_factor(Team& T, Ring*, const CholDev& C, const CholWork& W, const double* Pv, const double* dg,
-                                                     double shift, const double* w, const double* Jv, const double*, Prof& pf) {
+                                                     double shift, const double* w, const double* Jv, const double* b, Prof& pf) {
     chol_assemble(T, C, W, Pv, dg, shift, w, Jv, pf);
-    return chol_factor(T, C, W, pf);
+    return chol_factor(T, C, W, pf, b);
 }
 __device__ __forceinline__ bool team_assemble_factor(CtaTeam& T, Ring* R, const CholDev& C, const CholWork& W, const double* Pv,
                                                      const double* dg, double shift, const double* w, const double* Jv,
                                                      const double* b, Prof& pf) {
     if (R) return chol_assemble_factor_fwd_ring(T, *R, C, W, Pv, dg, shift, w, Jv, b, pf);
     chol_assemble(T, C, W, Pv, dg, shift, w, Jv, pf);
-    return chol_factor(T, C, W, pf);
+    return chol_factor(T, C, W, pf, b);
 }
 template <class Team>
 __device__ __forceinline__ void team_solve(Team& T, Ring*, const CholDev& C, const CholWork& W, const double* b, double* x, Prof& pf) {
-    chol_solve(T, C, W, b, x, pf);
+    chol_solve(T, C, W, b, x, pf, C.fused_fwd != 0);
 }
 __device__ __forceinline__ void team_solve(CtaTeam& T, Ring* R, const CholDev& C, const CholWork& W, const double* b, double* x, Prof& pf) {
     if (R) chol_backsolve_ring(T, *R, C, W, x, pf);
-    else chol_solve(T, C, W, b, x, pf);
+    else chol_solve(T, C, W, b, x, pf, C.fused_fwd != 0);
 }
 
 template <bool RING, class Team>
@@ -294,7 +294,8 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
             T.sync();
             pf.lap(PS_RHS);
         };
-        if (R) build_rhs();  // ring mode: the forward sweep of the Newton solve rides in the factorisation's chunks
+        const bool rhs_first = R || C.fused_fwd;  // the forward sweep of the Newton solve rides in the factorisation's phases
+        if (rhs_first) build_rhs();
         // ---- assembly, factorisation (with inertia correction: the shift rho_p is a scalar on the diagonal) ----
         bool fact_ok = false;
         for (int tries = 0; tries < 30 && !fact_ok; ++tries) {
@@ -313,7 +314,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         out.rho_p = rho_p;
 
         // ---- P3 / P4: right-hand side, Newton solve ----------------------------------------------------
-        if (!R) build_rhs();
+        if (!rhs_first) build_rhs();
         team_solve(T, R, C, W, I.nv[N_P], I.nv[N_XT], pf);
         // ---- P5: J dx and the step-to-boundary ratio ------------------------------------------------------
         double ratio[1] = {0.0};

@@ -59,6 +59,7 @@ struct sqpqp_handle_s {
     int64_t launches = 0;
     cudaError_t async_err = cudaSuccess;  // first failure of a staged copy (upload / download); reported by finish() / the caller
     int tail_override = -1;               // development knob (sqpqp_debug_set what = 1): cap of the dense tail in columns
+    int fuse_fwd = 1;                     // what = 7: 0 keeps the forward sweep out of the factor program (slot lists); at setup
     int ring_enable = 1;                  // sqpqp_debug_set what = 5: 0 keeps the slot lists (no ring programs are built); at setup
     bool last_ring = false;
     // caller buffers page-locked with sqpqp_host_register: copied to / from the device directly, without the pinned staging hop
@@ -547,6 +548,7 @@ extern "C" int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value) {  /
     if (what == 3 && (value == 0 || value == 256 || value == 512 || value == 1024)) h->ilv_threads = value;
     if (what == 4 && value >= 0 && value <= 2) h->ilv_occ = value;
     if (what == 5) h->ring_enable = value != 0;
+    if (what == 7) h->fuse_fwd = value != 0;
     if (what == 6 && value >= 0 && value <= 2) h->ring_mode = value;
     return 0;
 }
@@ -771,6 +773,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         const bool grid_mode = batch == 1 && (size_t)P.Ne + m > 6000;
         auto upload_symbolic = [&](Symbolic& Sy, CholDev& C, int ncols, bool hasP) -> int {
             C.n = ncols; C.nnzL = Sy.nnzL; C.nlev = Sy.nlev; C.n0 = Sy.n0; C.T = Sy.T;
+            C.fused_fwd = Sy.fused_fwd ? 1 : 0;
             C.Tpad = grid_mode ? ((Sy.T + GD_NB - 1) / GD_NB) * GD_NB : ((Sy.T + 3) & ~3);
             C.nphase = (int)Sy.fphase.size() / 4; C.n_aslot = (int)Sy.aslot_d.size(); C.nslotJ = (int)Sy.jrow.size();
             for (int k = 0; k < 4; ++k) Sy.fphase.push_back(0);  // the phase loop reads one entry ahead
@@ -852,6 +855,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             SlotProg sp;
             build_slot_programs(Sy, 5 - lgG, h->ilv_nt / G, sp);
             X->C = base;
+            X->C.fused_fwd = 0;  // its own (unfused) slot lists
             X->C.nphase = (int)sp.fphase.size() / 4;
             X->C.n_aslot = (int)sp.aslot_d.size();
             for (int k = 0; k < 4; ++k) sp.fphase.push_back(0);
@@ -889,7 +893,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             h->planH = SpmvPlan{(int)blk.size() - 1, d, ph.row_ptr, ph.row_ptr + 1, ph.col_idx, n, n, P.nnzH};
         }
         DALLOC(P.wJ, B * (size_t)(P.nnzJ > 0 ? P.nnzJ : 1));
-        Symbolic Sy = symbolic_analyze(n, m, hJrb.data(), hJre.data(), hJc.data(), hHrp.data(), hHc.data(), 512, tail_cap(n));
+        Symbolic Sy = symbolic_analyze(n, m, hJrb.data(), hJre.data(), hJc.data(), hHrp.data(), hHc.data(), 512, tail_cap(n), h->fuse_fwd != 0);
         if (Sy.ok && (int64_t)Sy.fp_ab.size() < ((int64_t)1 << 29) && Sy.nnzL < (1 << 26)) {
             int rc2 = upload_symbolic(Sy, P.chol, n, true);
             if (rc2) return rc2;
@@ -909,7 +913,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
         // feasibility-restoration LP: columns [J | S], no quadratic term
         P.has_chol_fr = 0;
         if (S > 0 && m > 0) {
-            Symbolic Sf = symbolic_analyze(P.Ne, m, hJrb.data(), hJrb.data() + 1, hJc.data(), nullptr, nullptr, 512, tail_cap(P.Ne));
+            Symbolic Sf = symbolic_analyze(P.Ne, m, hJrb.data(), hJrb.data() + 1, hJc.data(), nullptr, nullptr, 512, tail_cap(P.Ne), h->fuse_fwd != 0);
             if (Sf.ok && (int64_t)Sf.fp_ab.size() < ((int64_t)1 << 29) && Sf.nnzL < (1 << 26)) {
                 int rc2 = upload_symbolic(Sf, P.chol_fr, P.Ne, false);
                 if (rc2) return rc2;

@@ -47,6 +47,13 @@ struct Symbolic {
     //           (descending): lane groups are then aligned to their own (power of two) size inside a warp.
     std::vector<int> ftask, fphase;
     int ftasks = 0;                      // number of tasks (entries) behind the slots
+    // fused forward sweep (fuse_fwd): the right-hand side of the Newton solve is known before the factorisation, and row j of
+    // the forward sweep needs what the sub-diagonal entries of column j need (the pivot of j, finished lower levels), so its
+    // tasks ride in the same phase -- one barrier phase per level saved; the tail right-hand side rides with the Schur
+    // complement.  A sweep slot has bit 31 set, target = row j, aux = j, and its pairs (value index, row) are the CSR entries
+    // of row j, appended to fp_ab at pair offset sw_off.
+    bool fused_fwd = false;
+    int sw_off = 0;
     // assembly: K_e = P[h] + sum_t wJ[a_t] * Jv[b_t]  (+ d[perm[j]] on the diagonal), wJ = w[row] .* Jv
     // assembly slots, same lane-group scheme as the factor slots (a diagonal entry of a bus variable has 40+ terms, most
     // sourced entries have one or two):  slot = (entry id | lg << 26 | leader << 29, first term of this lane, end term,
@@ -70,12 +77,12 @@ struct SlotProg {
     std::vector<int> ftask, fphase, aslot, aslot_d;
     int ftasks = 0, atasks = 0;
 };
-inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, SlotProg& out);
+inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, SlotProg& out, bool fuse_fwd = false);
 
 // J: m x ncols CSR (rb/re per row, so a prefix of each row can be used), P: symmetric-full CSR or null.
 // tail_max: largest dense tail (columns) the caller can hold; 0 disables the dense tail.
 inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, const int* Jcol, const int* Prp,
-                                 const int* Pcol, int max_row_len = 512, int tail_max = 0) {
+                                 const int* Pcol, int max_row_len = 512, int tail_max = 0, bool fuse_fwd = false) {
     Symbolic S;
     S.n = n;
     // ---- 1. adjacency of K ---------------------------------------------------------------
@@ -284,8 +291,13 @@ inline Symbolic symbolic_analyze(int n, int m, const int* Jrb, const int* Jre, c
     }
     // ---- 4c. slot lists of the assembly and the factorisation phases (CTA team: 32 lanes per task at most) ----------
     {
+        if (fuse_fwd) {  // the sweep tasks take their pairs from the CSR of L, appended behind the factor pairs
+            S.fused_fwd = true;
+            S.sw_off = (int)(S.fp_ab.size() / 2);
+            S.fp_ab.insert(S.fp_ab.end(), S.Rci.begin(), S.Rci.end());
+        }
         SlotProg sp;
-        build_slot_programs(S, 5, 512, sp);
+        build_slot_programs(S, 5, 512, sp, fuse_fwd);
         S.ftask.swap(sp.ftask); S.fphase.swap(sp.fphase); S.aslot.swap(sp.aslot); S.aslot_d.swap(sp.aslot_d);
         S.ftasks = sp.ftasks; S.atasks = sp.atasks;
     }
@@ -492,7 +504,7 @@ inline void build_ring_program(const Symbolic& S, bool has_P, int ns_max, int kc
     out.ok = out.seg_count[0] > 0 && out.seg_count[1] > 0 && out.seg_count[2] > 0;
 }
 
-inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, SlotProg& out) {
+inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, SlotProg& out, bool fuse_fwd) {
     const int n = S.n, n0 = S.n0;
     out = SlotProg();
     // ---- assembly slots (4b) -------------------------------------------------------------------------------------
@@ -517,7 +529,7 @@ inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, Sl
         }
     }
     // ---- factorisation phases (4c) ---------------------------------------------------------------------------------
-    struct Tk { int tgt, q0, q1, aux; };
+    struct Tk { int tgt, q0, q1, aux; bool sw = false; };
     auto emit = [&](std::vector<Tk>& v, int kind) {
         std::stable_sort(v.begin(), v.end(), [](const Tk& a, const Tk& b) { return a.q1 - a.q0 > b.q1 - b.q0; });
         std::vector<int> lg(v.size(), 0);
@@ -541,7 +553,8 @@ inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, Sl
         for (size_t t = 0; t < v.size(); ++t) {
             const Tk& k = v[t];
             for (int lane = 0; lane < (1 << lg[t]); ++lane) {
-                out.ftask.push_back(k.tgt | (lg[t] << 26) | (lane == 0 ? (1 << 29) : 0) | (S.hasK[k.tgt] ? (1 << 30) : 0));
+                out.ftask.push_back(k.sw ? (int)((unsigned)k.tgt | ((unsigned)lg[t] << 26) | (lane == 0 ? (1u << 29) : 0u) | (1u << 31))
+                                         : (k.tgt | (lg[t] << 26) | (lane == 0 ? (1 << 29) : 0) | (S.hasK[k.tgt] ? (1 << 30) : 0)));
                 out.ftask.push_back(k.q0 + lane); out.ftask.push_back(k.q1); out.ftask.push_back(k.aux);
             }
             mp = std::max(mp, k.q1 - k.q0);
@@ -556,8 +569,10 @@ inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, Sl
     for (int l = 0; l < S.nlev; ++l) {
         for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j) v.push_back(Tk{S.Lp[j], S.fp_ptr[S.Lp[j]], S.fp_ptr[S.Lp[j] + 1], j});
         emit(v, 0);
-        for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j)
+        for (int j = S.lev_ptr[l]; j < S.lev_ptr[l + 1]; ++j) {
             for (int e = S.Lp[j] + 1; e < S.Lp[j + 1]; ++e) v.push_back(Tk{e, S.fp_ptr[e], S.fp_ptr[e + 1], j});
+            if (fuse_fwd) { Tk t{j, S.sw_off + S.Rp[j], S.sw_off + S.Rp[j + 1], j}; t.sw = true; v.push_back(t); }
+        }
         if (!v.empty()) emit(v, 1);
     }
     if (S.T > 0) {
@@ -567,6 +582,9 @@ inline void build_slot_programs(const Symbolic& S, int lgmax, int team_lanes, Sl
                 int r = S.Li[e] - n0, c = j - n0;
                 v.push_back(Tk{e, S.fp_ptr[e], S.fp_ptr[e + 1], r * (r + 1) / 2 + c});
             }
+        if (fuse_fwd)  // right-hand side of the tail: yw[j] -= sum over the sparse columns
+            for (int j = n0; j < n; ++j)
+                if (S.Rmid[j] > S.Rp[j]) { Tk t{j, S.sw_off + S.Rp[j], S.sw_off + S.Rmid[j], j}; t.sw = true; v.push_back(t); }
         emit(v, 2);
     }
 }

@@ -11,11 +11,12 @@
 
 static inline int tri(int r) { return r * (r + 1) / 2; }
 
-extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, const double* Jv, const int* Prp, const int* Pcol,
+extern "C" int symcheck_solve3(int n, int m, const int* Jrp, const int* Jcol, const double* Jv, const int* Prp, const int* Pcol,
                                const double* Pv, const double* d, const double* w, const double* rhs, double* x,
-                               int64_t* stats /* nnzL, sparse levels, flops, assembly terms, tail, tree levels */, int tail_max) {
-    Symbolic S = symbolic_analyze(n, m, Jrp, Jrp + 1, Jcol, Prp, Pcol, 512, tail_max);
+                               int64_t* stats /* nnzL, sparse levels, flops, assembly terms, tail, tree levels */, int tail_max, int fuse) {
+    Symbolic S = symbolic_analyze(n, m, Jrp, Jrp + 1, Jcol, Prp, Pcol, 512, tail_max, fuse != 0);
     if (!S.ok) return -1;
+    if ((fuse != 0) != S.fused_fwd) return -12;
     const int n0 = S.n0, T = S.T;
     std::vector<double> L(S.nnzL, std::nan("")), D((size_t)tri(T) + T, 0.0), dinv(n), wJ(S.jrow.size());
     if (S.nnzL >= (1 << 26)) return -9;  // slot encoding: 26 bits of entry id
@@ -38,24 +39,42 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
     }
     // factorisation phases (chol_factor).  done[e] = phase that produced entry e: a task may only read entries of
     // EARLIER phases (the device runs the tasks of one phase concurrently).
-    std::vector<int> done(S.nnzL, 1 << 30), ddone(n, 1 << 30);
+    std::vector<int> done(S.nnzL, 1 << 30), ddone(n, 1 << 30), ydone(n, fuse ? (1 << 30) : -1);
+    std::vector<double> y(n);
+    for (int k = 0; k < n; ++k) y[k] = rhs[S.perm[k]];
     for (size_t p = 0; p < S.fphase.size() / 4; ++p) {
         const int* ph = &S.fphase[4 * p];
         for (int t = ph[0]; t < ph[1];) {
             const int* tk = &S.ftask[4 * (size_t)t];
             const int e = tk[0] & 0x3ffffff, Ln = 1 << ((tk[0] >> 26) & 7);
+            const bool sw = tk[0] < 0;                          // forward-sweep slot of a fused program
+            if (sw && !fuse) return -13;
             if (!((tk[0] >> 29) & 1)) return -6;                // a task starts with its leader slot
             if ((t - ph[0]) % Ln != 0) return -7;               // lane groups aligned to their size
             double acc = 0.0;
             int npairs = 0;
             for (int lane = 0; lane < Ln; ++lane) {             // the lanes of the task, each with stride Ln
                 const int* sl = &S.ftask[4 * (size_t)(t + lane)];
-                if ((sl[0] & 0x3ffffff) != e || sl[1] != tk[1] + lane || (lane > 0 && ((sl[0] >> 29) & 1))) return -8;
+                if ((sl[0] & 0x3ffffff) != e || sl[1] != tk[1] + lane || (lane > 0 && ((sl[0] >> 29) & 1)) || ((sl[0] < 0) != sw)) return -8;
                 for (int q = sl[1]; q < sl[2]; q += Ln, ++npairs) {
                     const int ea = S.fp_ab[2 * (size_t)q], eb = S.fp_ab[2 * (size_t)q + 1];
-                    if (done[ea] >= (int)p || done[eb] >= (int)p) return -10;  // intra-phase dependency
-                    acc += L[ea] * L[eb];
+                    if (sw) {
+                        if (done[ea] >= (int)p || ydone[eb] >= (int)p) return -10;
+                        acc += L[ea] * y[eb];
+                    } else {
+                        if (done[ea] >= (int)p || done[eb] >= (int)p) return -10;  // intra-phase dependency
+                        acc += L[ea] * L[eb];
+                    }
                 }
+            }
+            if (sw) {  // row e of the forward sweep (levels) or the right-hand side of the tail (Schur phase)
+                if (npairs != tk[2] - tk[1]) return -5;
+                if (ph[3] == 1) { if (ddone[e] >= (int)p) return -11; y[e] = (y[e] - acc) * dinv[e]; }
+                else if (ph[3] == 2) y[e] -= acc;
+                else return -14;
+                ydone[e] = (int)p;
+                t += Ln;
+                continue;
             }
             if (npairs != tk[2] - tk[1] || npairs > (ph[2] & 0xffffff)) return -5;  // ph[2] = max pairs | max lg << 24
             double v = ((tk[0] >> 30) & 1 ? L[e] : 0.0) - acc;
@@ -91,15 +110,15 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
             }
         }
     }
-    std::vector<double> y(n);
-    for (int k = 0; k < n; ++k) y[k] = rhs[S.perm[k]];
-    for (int j = 0; j < n0; ++j) {
+    for (int j = 0; j < n0 && !fuse; ++j) {
         double acc = 0.0;
         for (int q = S.Rp[j]; q < S.Rp[j + 1]; ++q) acc += L[S.Rci[2 * (size_t)q]] * y[S.Rci[2 * (size_t)q + 1]];
         y[j] = (y[j] - acc) * dinv[j];
     }
+    if (fuse)
+        for (int j = 0; j < n0; ++j) if (ydone[j] > (1 << 29)) return -15;  // every row of the sparse levels was swept
     if (T > 0) {
-        for (int j = n0; j < n; ++j) {
+        for (int j = n0; j < n && !fuse; ++j) {
             double acc = 0.0;
             for (int q = S.Rp[j]; q < S.Rmid[j]; ++q) acc += L[S.Rci[2 * (size_t)q]] * y[S.Rci[2 * (size_t)q + 1]];
             y[j] -= acc;
@@ -125,6 +144,12 @@ extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, co
         stats[4] = S.T; stats[5] = S.nlev_total;
     }
     return 0;
+}
+
+extern "C" int symcheck_solve2(int n, int m, const int* Jrp, const int* Jcol, const double* Jv, const int* Prp, const int* Pcol,
+                               const double* Pv, const double* d, const double* w, const double* rhs, double* x, int64_t* stats,
+                               int tail_max) {
+    return symcheck_solve3(n, m, Jrp, Jcol, Jv, Prp, Pcol, Pv, d, w, rhs, x, stats, tail_max, 0);
 }
 
 extern "C" int symcheck_solve(int n, int m, const int* Jrp, const int* Jcol, const double* Jv, const int* Prp, const int* Pcol,

@@ -29,7 +29,7 @@ def symlib():
     return C.CDLL(out)
 
 
-def _solve(lib, J, P, d, w, rhs, tail_max=0):
+def _solve(lib, J, P, d, w, rhs, tail_max=0, fuse=0):
     J = sp.csr_matrix(J); J.sort_indices()
     n, m = J.shape[1], J.shape[0]
     ip = C.POINTER(C.c_int32); dp = C.POINTER(C.c_double)
@@ -39,11 +39,11 @@ def _solve(lib, J, P, d, w, rhs, tail_max=0):
         P = sp.csr_matrix(P); P.sort_indices()
         prp, pc, pv = a(P.indptr, np.int32), a(P.indices, np.int32), a(P.data, np.float64)
     x = np.zeros(n); stats = np.zeros(6, dtype=np.int64)
-    rc = lib.symcheck_solve2(n, m, jrp.ctypes.data_as(ip), jc.ctypes.data_as(ip), jv.ctypes.data_as(dp),
+    rc = lib.symcheck_solve3(n, m, jrp.ctypes.data_as(ip), jc.ctypes.data_as(ip), jv.ctypes.data_as(dp),
                             prp.ctypes.data_as(ip) if P is not None else None, pc.ctypes.data_as(ip) if P is not None else None,
                             pv.ctypes.data_as(dp) if P is not None else None, a(d, np.float64).ctypes.data_as(dp),
                             a(w, np.float64).ctypes.data_as(dp), a(rhs, np.float64).ctypes.data_as(dp), x.ctypes.data_as(dp),
-                            stats.ctypes.data_as(C.POINTER(C.c_int64)), int(tail_max))
+                            stats.ctypes.data_as(C.POINTER(C.c_int64)), int(tail_max), int(fuse))
     return rc, x, stats
 
 
@@ -59,15 +59,17 @@ def test_random_patterns(symlib):
         rhs = rng.standard_normal(n)
         K = P.toarray() + np.diag(d) + J.T.toarray() @ np.diag(w) @ J.toarray()
         for tail_max in (0, 24, 128):  # plain level-scheduled code / dense tail of the top levels
-            rc, x, stats = _solve(symlib, J, P, d, w, rhs, tail_max)
-            assert rc == 0
-            assert np.abs(K @ x - rhs).max() <= 1e-10 * max(1.0, np.abs(rhs).max()), (n, m, tail_max)
-            assert stats[4] <= tail_max
+            for fuse in (0, 1):        # forward sweep on its own / riding in the factor phases
+                rc, x, stats = _solve(symlib, J, P, d, w, rhs, tail_max, fuse)
+                assert rc == 0, (n, m, tail_max, fuse, rc)
+                assert np.abs(K @ x - rhs).max() <= 1e-10 * max(1.0, np.abs(rhs).max()), (n, m, tail_max, fuse)
+                assert stats[4] <= tail_max
 
 
+@pytest.mark.parametrize("fuse", [0, 1])
 @pytest.mark.parametrize("tail_max", [0, 92])
 @pytest.mark.parametrize("make", [lambda: AcopfPolar(case9()), lambda: AcopfPolar(synth_net(118, 186, 54, 118))])
-def test_acopf_patterns_and_fill(symlib, make, tail_max):
+def test_acopf_patterns_and_fill(symlib, make, tail_max, fuse):
     nlp = make()
     rng = np.random.default_rng(1)
     J = CooMatrix(nlp.j_row, nlp.j_col, nlp.m, nlp.n); J.fill(rng.standard_normal(nlp.nnz_jac_coo)); Js = J.to_scipy()
@@ -75,7 +77,7 @@ def test_acopf_patterns_and_fill(symlib, make, tail_max):
     d = np.abs(Hs).sum(axis=1).A1 + 1e-3
     w = rng.uniform(0.0, 1e4, nlp.m)
     rhs = rng.standard_normal(nlp.n)
-    rc, x, stats = _solve(symlib, Js, Hs, d, w, rhs, tail_max)
+    rc, x, stats = _solve(symlib, Js, Hs, d, w, rhs, tail_max, fuse)
     assert rc == 0
     K = (Hs + sp.diags(d) + Js.T @ sp.diags(w) @ Js).toarray()
     ref = np.linalg.solve(K, rhs)

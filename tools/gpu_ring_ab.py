@@ -13,9 +13,11 @@ B = int(sys.argv[1]); rounds = int(sys.argv[2])
 capi.build()
 net = synth_net(118, 186, 54, 118)
 pd, qd = net.perturbed_loads(B)
-cfgs = [("default", None, 0), ("occ1 slot lists", dict(occupancy=1), 1), ("occ1 ring", dict(occupancy=1), 2)]
-for name, eo, ring in cfgs:
-    sqp = BatchSqpTR(AcopfPolar(net, pd=pd, qd=qd), B, Parameters(max_iter=rounds, init_mu=1e5), engine_options=eo)
+cfgs = [("default", None, 0, None), ("default unfused", None, 0, dict(fuse=0)), ("occ1 slot lists", dict(occupancy=1), 1, None), ("occ1 ring", dict(occupancy=1), 2, None)]
+if len(sys.argv) > 3:
+    cfgs = [c for c in cfgs if c[0] in sys.argv[3:]]
+for name, eo, ring, layout in cfgs:
+    sqp = BatchSqpTR(AcopfPolar(net, pd=pd, qd=qd), B, Parameters(max_iter=rounds, init_mu=1e5), engine_options=eo, layout=layout)
     eng = sqp.optimizer.engine
     eng.set_layout(ring=ring)
     ms, its = [], []
