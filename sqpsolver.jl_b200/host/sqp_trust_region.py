@@ -76,6 +76,11 @@ class BatchSqpTR:
         self.n_qp = np.zeros(B, np.int64)
         self.optimizer = QpDevice(nlp, batch=B, device=device, engine_options=engine_options, layout=layout)
         self.optimizer.create_model(None)
+        # the persistent vectors of the SQP object (sqp.jl:16-59) are page-locked once, so that every call copies them straight
+        # over the link (sqpqp_host_register); not worth it for a single small instance
+        if B * max(n, m) >= (1 << 16):
+            self.optimizer.engine.register_host(self.x, self.p, self.lam, self.mult_x_L, self.mult_x_U, self.df, self.E,
+                                                self.dE, self.h_val)
         # f, grad f, g and the J / H COO values evaluated on the device (csrc/acopf.cuh) instead of by the
         # host callbacks -- only x and lambda go up, only f, E, grad f come back
         self.device_evaluator = bool(device_evaluator)

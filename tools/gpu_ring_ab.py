@@ -34,5 +34,6 @@ for name, eo, ring, layout in cfgs:
     sqp.optimizer._solve = hook
     sqp.run()
     st = {int(k): int(v) for k, v in zip(*np.unique(sqp.status, return_counts=True))}
-    print(f"{name:18s} kernel {eng.last_solve_kernel:28s} ms/round " + " ".join(f"{m:6.1f}" for m in ms) + f"   total {sum(ms):7.1f}   iters(mean,max) {its[-1]}  status {st}", flush=True)
+    shown = ms if len(ms) <= 10 else ms[:4] + ms[-4:]
+    print(f"{name:18s} kernel {eng.last_solve_kernel:28s} ms/round " + " ".join(f"{m:6.1f}" for m in shown) + f"   total {sum(ms):7.1f} over {len(ms)} launches   late half {sum(ms[len(ms)//2:]):7.1f}   iters(mean,max) last {its[-1]} max-of-max {max(i[1] for i in its)}  status {st}", flush=True)
     sqp.close()
