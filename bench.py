@@ -541,7 +541,7 @@ def main():
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
-            if tr.get("kernel") == kernel_name and tr.get("batch_per_gpu") == Bl and tr.get("workload") == args.workload:
+            if kernel_name.startswith(tr.get("kernel", "?")) and tr.get("batch_per_gpu") == Bl and tr.get("workload") == args.workload:
                 traffic = tr
         except (OSError, ValueError):
             pass

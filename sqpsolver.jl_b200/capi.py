@@ -249,7 +249,7 @@ class Engine:
             setattr(self.opts, k, v)
         self._ck(self.L.sqpqp_set_options(self.h, C.byref(self.opts)))
 
-    def set_layout(self, G=0, threads=0, ctas_per_sm=0, tail=-1, ring=None, fuse=None):
+    def set_layout(self, G=0, threads=0, ctas_per_sm=0, tail=-1, ring=None, fuse=None, handoff=None):
         """Layout of the batched interior-point launch, effective at the next setup_nlp: G instances interleaved per CTA
         (0 = auto, 1 = one CTA per instance, 2 / 4 / 8), its CTA size (0 = auto, 256 / 512 / 1024), CTAs per SM
         (0 = auto) and the cap of the dense tail of the factor in columns (-1 = auto).  ring (effective at the next solve):
@@ -259,6 +259,8 @@ class Engine:
             self._ck(self.L.sqpqp_debug_set(self.h, what, int(v)))
         if ring is not None:
             self._ck(self.L.sqpqp_debug_set(self.h, 6, int(ring)))
+        if handoff is not None:  # iteration quota before the resident launch takes an instance over (-1 auto, 0 off)
+            self._ck(self.L.sqpqp_debug_set(self.h, 8, int(handoff)))
         if fuse is not None:  # (next setup_nlp) 0: forward sweep of the Newton solve as its own level-scheduled pass
             self._ck(self.L.sqpqp_debug_set(self.h, 7, int(fuse)))
 

@@ -24,6 +24,9 @@
 
 struct DevOpts {
     sqpqp_options o;
+    int handoff_k;   // > 0: an interior-point solve that has not finished after this many iterations saves its state and is
+                     //      flagged 3 for the resident launch that follows (stragglers finish there at lower latency)
+    int resume;      // 1: this launch continues the instances flagged 3 and skips all others
 };
 
 // A work-vector slot resolved to its address at the point of use, from kernel parameters (constant
@@ -43,6 +46,7 @@ struct VecTab {
         }
         return base[k] + inst_off;
     }
+    __device__ __forceinline__ double* global(int k) const { return base[k] + inst_off; }  // the slot's home in global memory
 };
 
 // resolved per-instance views
@@ -188,13 +192,14 @@ __device__ void set_rho(Team& T, const Inst& I, const sqpqp_options& o, double r
 
 // interior-point path (ipm.cuh)
 struct IpmOut {
-    bool solved, almost, infeasible, blowup;
+    bool solved, almost, infeasible, blowup, handoff;
     int iters, nfact;
     double rp, rd, rho_p;
 };
 template <bool RING, class Team>
 __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, Ring* R, const sqpqp_options& o,
-                          double c, int phase, const double* xk_scaled_start);
+                          double c, int phase, const double* xk_scaled_start, int handoff_k = 0, IpmState* st = nullptr,
+                          bool resume = false);
 __device__ __forceinline__ void ring_init(Ring& R, const CholDev& C, const CholWork& W, int stage0_dbl, unsigned long long* bars);
 
 // ---------------------------------------------------------------------------------------
@@ -218,9 +223,13 @@ __device__ __forceinline__ void ring_init(Ring& R, const CholDev& C, const CholW
 // compiled out of the other variants, where its registers would turn into spills)
 template <int MODE, class Team, bool RING = false>
 __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, int inst, int phase,
-                               const Placement* pl, double* dsm, unsigned long long* rbar = nullptr) {
+                               const Placement* pl, double* dsm, unsigned long long* rbar = nullptr, int handoff_k = 0,
+                               bool resume = false) {
     if constexpr (MODE == 2) {
         if (o.method != 1 && P.fb_flag[inst] == 0) return;  // uniform per team: solved by the interior-point launch
+    }
+    if constexpr (MODE == 1) {
+        if (resume && P.fb_flag[inst] != 3) return;         // the resident launch only continues what was handed over
     }
     Prof pfo;
     pfo.start();
@@ -393,7 +402,7 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
             if (pl->dtail >= 0) { W.D = dsm + pl->dtail; W.col = dsm + pl->dcol; }
         }
         const double* start = nullptr;
-        if (phase == SQPQP_PHASE_LP) {
+        if (phase == SQPQP_PHASE_LP && !resume) {
             double *x = I.nv[N_X], *D = I.nv[N_D];
             for_n(T, N, [&](int j) { x[j] = xk[j] / D[j]; });
             T.sync();
@@ -409,8 +418,13 @@ __device__ void solve_instance(Team& T, const Prob& P, const sqpqp_options& o, i
             }
         }
         pfo.lap(PS_PROLOGUE);
-        IpmOut io = ipm_run<RING>(T, I, CD, W, (RING && R.on) ? &R : (Ring*)nullptr, o, c, phase, start);
+        IpmOut io = ipm_run<RING>(T, I, CD, W, (RING && R.on) ? &R : (Ring*)nullptr, o, c, phase, start, handoff_k,
+                                  (handoff_k > 0 || resume) ? P.ipm_state + inst : (IpmState*)nullptr, resume);
         pfo.start();
+        if (io.handoff) {  // quota used up: state saved, the resident launch continues this instance
+            if (T.tid() == 0) P.fb_flag[inst] = 3;
+            return;
+        }
         ipm_iters = io.iters;
         nfact = io.nfact;
         ipm_blowup = io.blowup;
@@ -835,7 +849,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(const __grid_constant_
     for (int inst = blockIdx.x; inst < P.batch; inst += gridDim.x) {
         if (P.active && !P.active[inst]) continue;
         CtaTeam T(sh);
-        solve_instance<MODE, CtaTeam, (MINB == 1 && MODE == 1)>(T, P, O.o, inst, phase, &pl, dsm, rbar);
+        solve_instance<MODE, CtaTeam, (MINB == 1 && MODE == 1)>(T, P, O.o, inst, phase, &pl, dsm, rbar, MODE == 1 ? O.handoff_k : 0,
+                                                                MODE == 1 && O.resume != 0);
         __syncthreads();
     }
 }

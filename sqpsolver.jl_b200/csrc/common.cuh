@@ -79,6 +79,14 @@ struct CholWork {
     int oL, oyw, odinv, oD;  // ring mode: the same four arrays as offsets (doubles) into the CTA's dynamic shared memory
 };
 
+// Interior-point state of an instance the throughput launch handed over after its iteration quota (launch_solve: hand-off):
+// the scalars of the loop; the iterate itself (x, slacks, multipliers, tracked residuals, last direction) is in the
+// per-instance work vectors in global memory.
+struct IpmState {
+    double delta, rho_p, rho_last, mu_t, alpha, sig_prev, del_prev, rp_ref, nin;
+    int it, nfact, acc_cnt, pad;
+};
+
 struct Prob {
     int n, m, mlin, S, Ne, batch;
     int nnzJ, nnzT, nnzH;         // slots per instance (J ext, its transpose, H symmetric)
@@ -106,7 +114,9 @@ struct Prob {
     // outputs
     double *o_p, *o_lam, *o_mxL, *o_mxU, *o_slack;
     sqpqp_info* o_info;
-    int* fb_flag;                // [batch] 0 solved by the interior-point launch, 1 needs the ADMM launch, 2 ditto after a blow-up
+    int* fb_flag;                // [batch] 0 solved by the interior-point launch, 1 needs the ADMM launch, 2 ditto after a blow-up,
+                                 //         3 handed over to the resident launch after its iteration quota (state in ipm_state)
+    IpmState* ipm_state;         // [batch]
     // interior-point path: symbolic Cholesky (null n = unavailable), per-instance factor values
     // [batch][nnzL] and permuted solve scratch [batch][n]
     CholDev chol;      // QP / SOC / LP-projection phases: n columns, P = H or 2I

@@ -59,7 +59,7 @@ __device__ __forceinline__ void team_solve(CtaTeam& T, Ring* R, const CholDev& C
 
 template <bool RING, class Team>
 __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWork& W, Ring* Rin, const sqpqp_options& o,
-                          double c, int phase, const double* xk_scaled_start) {
+                          double c, int phase, const double* xk_scaled_start, int handoff_k, IpmState* st, bool resume) {
     Ring* const R = RING ? Rin : (Ring*)nullptr;  // a compile-time null outside the resident launch: the ring code folds away
     const int N = I.N, M = I.M;
     // Work vectors are slots of the ADMM workspace (the two methods never run concurrently), addressed through
@@ -71,9 +71,25 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
     // Side residuals are TRACKED (r += alpha (g dx + ds)), never recomputed from A x - b: at the end of the
     // solve delta ~ 1e-8 and a freshly evaluated residual carries ~1e-16 |Ax| of rounding noise, which the
     // dual update dy = (J dx + r)/delta would amplify by 1/delta.
-    IpmOut out{false, false, false, false, 0, 0, INFINITY, INFINITY, 0.0};
+    IpmOut out{false, false, false, false, false, 0, 0, INFINITY, INFINITY, 0.0};
     Prof pf;
     pf.start();
+    double cnt[1] = {0.0};
+    if (resume) {
+        // continue an instance another launch handed over: its iterate lives in the global work vectors; bring the parts this
+        // launch keeps in shared memory there (the scaled problem data was rebuilt, identically, by stage A)
+        const int stN[] = {N_X, N_ZB, N_YB, N_RB, N_KP, N_MASK, N_TMP2, N_I1, N_XT};
+        const int stM[] = {M_ZC, M_YC, M_RC, M_BC, M_I1, M_AX, M_I4, M_I3, M_I2};
+        for (int q = 0; q < 9; ++q) {
+            double* dst = I.nv[stN[q]];
+            const double* src = I.nv.global(stN[q]);
+            if (dst != src) for_n(T, N, [&](int j) { dst[j] = src[j]; });
+            double* dm = I.mv[stM[q]];
+            const double* sm = I.mv.global(stM[q]);
+            if (dm != sm) for_n(T, M, [&](int r) { dm[r] = sm[r]; });
+        }
+        T.sync();
+    } else {
     // ---- start point: I.nv[N_X] inside the box, unit duals, slacks >= 1 --------------------------------
     for_n(T, N, [&](int j) {
         double v = xk_scaled_start ? xk_scaled_start[j] : 0.0;
@@ -82,7 +98,6 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         I.nv[N_MASK][j] = 0.0;
     });
     T.sync();
-    double cnt[1] = {0.0};
     csr_rows(T, M, I.lgJ, I.J.rb, I.J.re, I.J.col, I.Jsv, I.nv[N_X], [&](int i, double ax) {
         bool eq = I.mv[M_RL][i] == I.mv[M_RU][i];
         bool uf = !eq && !isinf(I.mv[M_RU][i]), lf = !eq && !isinf(I.mv[M_RL][i]);
@@ -104,7 +119,8 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         cnt[0] += (double)uf + (double)lf;
     });
     T.template reduce<1, false>(cnt);
-    const double nin = fmax(cnt[0], 1.0);
+    }
+    const double nin = resume ? st->nin : fmax(cnt[0], 1.0);
 
     double delta = o.ipm_delta0, rho_p = o.ipm_rho0, rho_last = 0.0;
     int acc_cnt = 0;
@@ -122,10 +138,17 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
     //   P5  rows (CSR) / cols : J dx, step-to-boundary ratio
     double alpha = 0.0, sig_prev = 0.0, del_prev = delta;
     bool capped = true;  // cleared by every exit of the loop other than the iteration cap
-    for_n(T, M, [&](int i) { I.mv[M_I2][i] = 0.0; });
-    for_n(T, N, [&](int j) { I.nv[N_XT][j] = 0.0; });
+    int it0 = 0;
+    if (resume) {
+        delta = st->delta; rho_p = st->rho_p; rho_last = st->rho_last; mu_t = st->mu_t; alpha = st->alpha;
+        sig_prev = st->sig_prev; del_prev = st->del_prev; rp_ref = st->rp_ref; acc_cnt = st->acc_cnt;
+        it0 = st->it; out.nfact = st->nfact; out.iters = it0;
+    } else {
+        for_n(T, M, [&](int i) { I.mv[M_I2][i] = 0.0; });
+        for_n(T, N, [&](int j) { I.nv[N_XT][j] = 0.0; });
+    }
     T.sync();
-    for (int it = 0; it < o.ipm_max_iter; ++it) {
+    for (int it = it0; it < o.ipm_max_iter; ++it) {
         out.iters = it;
         double mx[8] = {0, 0, 0, 0, 0, 0, 0.0, -INFINITY};
         // [0] rp [1] rd*c [2] primal scale [3] dual scale*c [4] |A'lam|*c [5] |lam|*c (unscaled) [6] max s*z [7] max -(s*z)
@@ -357,9 +380,22 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         delta = fmax(o.ipm_delta_min, delta * 0.3);
         if (rho_p > o.ipm_rho0) rho_p = fmax(o.ipm_rho0, rho_p / 3.0);
         out.iters = it + 1;
+        if (handoff_k > 0 && it + 1 >= handoff_k && it + 1 < o.ipm_max_iter) {
+            // iteration quota of the throughput launch used up: the loop state goes to global memory (the vectors are there
+            // already: this launch keeps no work vector in shared memory) and the resident launch takes over at iteration it + 1
+            if (T.tid() == 0) {
+                st->delta = delta; st->rho_p = rho_p; st->rho_last = rho_last; st->mu_t = mu_t; st->alpha = alpha;
+                st->sig_prev = sig_prev; st->del_prev = del_prev; st->rp_ref = rp_ref; st->nin = nin;
+                st->it = it + 1; st->nfact = out.nfact; st->acc_cnt = acc_cnt;
+            }
+            out.handoff = true;
+            capped = false;
+            break;
+        }
     }
     T.sync();
     if (R) ring_drain(*R);  // chunks requested ahead for an iteration that is not going to happen
+    if (out.handoff) return out;
     // Iteration cap reached while the iterate was at the acceptable level (100 x ipm_eps on every residual): returned as
     // ALMOST_LOCALLY_SOLVED, Ipopt's "solved to acceptable level".  Exits through a blow-up, a NaN or a failed
     // factorisation never promote an iterate (their acc_cnt belongs to an earlier iteration).

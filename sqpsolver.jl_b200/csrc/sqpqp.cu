@@ -59,6 +59,8 @@ struct sqpqp_handle_s {
     int64_t launches = 0;
     cudaError_t async_err = cudaSuccess;  // first failure of a staged copy (upload / download); reported by finish() / the caller
     int tail_override = -1;               // development knob (sqpqp_debug_set what = 1): cap of the dense tail in columns
+    int handoff = -1;                     // what = 8: iteration quota of the throughput launch before an instance is handed to the
+                                          // resident launch; -1 auto (40 when num_sms < batch <= 2 num_sms and the ring fits), 0 off
     int fuse_fwd = 1;                     // what = 7: 0 keeps the forward sweep out of the factor program (slot lists); at setup
     int ring_enable = 1;                  // sqpqp_debug_set what = 5: 0 keeps the slot lists (no ring programs are built); at setup
     bool last_ring = false;
@@ -549,6 +551,7 @@ extern "C" int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value) {  /
     if (what == 4 && value >= 0 && value <= 2) h->ilv_occ = value;
     if (what == 5) h->ring_enable = value != 0;
     if (what == 7) h->fuse_fwd = value != 0;
+    if (what == 8) h->handoff = value;
     if (what == 6 && value >= 0 && value <= 2) h->ring_mode = value;
     return 0;
 }
@@ -728,6 +731,7 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
     DALLOC(P.o_slack, B * (S > 0 ? S : 1));
     DALLOC(P.o_info, B);
     DALLOC(P.fb_flag, B);
+    DALLOC(P.ipm_state, B);
     DALLOC(h->d_dE, B * (size_t)nnz_j); DALLOC(h->d_hval, B * (size_t)nnz_h); DALLOC(h->d_df, B * n); DALLOC(h->d_E, B * (m > 0 ? m : 1));
     DALLOC(h->d_xk, B * n); DALLOC(h->d_delta, B); DALLOC(h->d_Eov, B * (m > 0 ? m : 1)); DALLOC(h->d_active, B);
     const size_t nb = bounds_per_instance ? B : 1;
@@ -1149,7 +1153,7 @@ static int pick_threads(sqpqp_handle h, int phase) {
 static int launch_solve(sqpqp_handle h, int phase) {
     Prob& P = h->P;
     const size_t B = P.batch;
-    DevOpts O{h->opts};
+    DevOpts O{h->opts, 0, 0};
     int team = h->opts.team;
     if (team == 0) team = (B == 1 && (size_t)P.Ne + P.m > 6000) ? 2 : 1;
     // a dense tail laid out for the CTA team (panels of 4, shared memory) cannot be run by the grid team and vice versa
@@ -1229,6 +1233,25 @@ static int launch_solve(sqpqp_handle h, int phase) {
         if (threads > 512) threads = 512;
         if (cfg == 4 && threads > 256) threads = 256;
         h->last_ring = pl.ring >= 0;
+        // Hand-off: the throughput launch (several CTAs per SM, values in L2, ~0.49 ms per interior-point iteration) stops an
+        // instance after `quota` iterations; the stragglers -- the few instances of a batch that need 2-4 x the mean -- are
+        // continued by a second, resident launch (one CTA per SM, ring, ~0.34 ms per iteration) that every other CTA leaves at once.
+        Placement pl2;
+        size_t dyn2 = 0;
+        int quota = 0;
+        if (ipm && cfg >= 2 && !(h->G > 1) && CD.ring_ok && h->ring_mode != 1 && h->opts.method != 1 && h->handoff != 0) {
+            place_arrays(P, phase, (size_t)h->max_dyn_smem, true, true, &pl2, true);
+            if (pl2.ring >= 0 && pl2.lval >= 0 && pl2.dinv >= 0 && pl2.yw >= 0 && (CD.T == 0 || pl2.dtail >= 0)) {
+                // measured (profiles/r02_tuning.md section 7): a gain only while the whole shard is co-resident in the throughput
+                // launch (B <= 2 x SMs: 256 instances 2 096 -> 1 940 ms over 60 rounds with a quota of 40); with several waves the
+                // block scheduler already overlaps the stragglers with the next wave and the second launch only adds a tail
+                // (1024 instances: 5 112 -> 5 320..5 390 ms)
+                quota = h->handoff > 0 ? h->handoff : (B <= (size_t)2 * h->num_sms ? 40 : 0);
+                if (quota >= h->opts.ipm_max_iter) quota = 0;
+                dyn2 = (size_t)pl2.total * sizeof(double);
+            }
+        }
+        O.handoff_k = quota;
         const bool use_ilv = ipm && h->G > 1 && (phase == SQPQP_PHASE_FR ? h->has_ilv_fr : h->has_ilv);
         if (use_ilv) {  // G instances interleaved per CTA (ilv.cuh); flags what it cannot finish for the ADMM launch below
             CUDA_OK(launch_ilv(h, O, phase, phase == SQPQP_PHASE_FR ? h->ilv_fr : h->ilv, phase == SQPQP_PHASE_FR ? h->ilv_fr_dyn : h->ilv_dyn));
@@ -1236,7 +1259,16 @@ static int launch_solve(sqpqp_handle h, int phase) {
             h->last_kernel = "k_solve_ilv<" + std::to_string(h->G) + "," + std::to_string(h->ilv_nt) + "," + std::to_string(h->ilv_minb) + ">";
         } else if (ipm) {
             launch(1);
+            if (quota > 0) {
+                DevOpts O2 = O;
+                O2.handoff_k = 0; O2.resume = 1;
+                int t2 = pick_threads(h, phase);
+                if (t2 > 512) t2 = 512;
+                k_solve_cta<512, 1, 1><<<grid, t2, dyn2, h->stream>>>(P, O2, phase, pl2);
+                h->launches++;
+            }
             h->last_kernel = cfg == 4 ? "k_solve_cta<256,4,1>" : (cfg == 2 ? (threads <= 384 ? "k_solve_cta<384,2,1>" : "k_solve_cta<512,2,1>") : (pl.ring >= 0 ? "k_solve_cta<512,1,1>+ring" : "k_solve_cta<512,1,1>"));
+            if (quota > 0) h->last_kernel += "+handoff";
         } else {  // no factorisation available: every instance is "flagged" (non-zero) for the ADMM launch
             h->last_kernel = "k_solve_cta<..,2> (ADMM)";
             CUDA_OK(cudaMemsetAsync(P.fb_flag, 1, B * sizeof(int), h->stream));

@@ -90,3 +90,48 @@ def test_ring_is_bit_reproducible_and_batched(built_lib):
             t["b"] = None
         s = cl.check_trace(AcopfPolar(net, pd=pd[b], qd=qd[b]), tr, oracle_every=2)
         assert s["worst_kkt"] <= 1e-6 and s["marginal_mismatch"] <= 1, (b, s)
+
+
+def test_handoff_to_the_resident_launch_matches_the_uninterrupted_solve(built_lib):
+    """Hand-off (launch_solve): the throughput launch stops every instance after its iteration quota, saves the loop state, and
+    the resident ring launch continues it.  With a quota of 10 nearly every instance changes kernels mid-solve; the result must
+    be the solve the uninterrupted launch gives: same classification, KKT points to 1e-6, the same step where the QP has one
+    solution, nearly the same iteration count (the two kernels sum the factorisation in a different order)."""
+    B = 200  # more instances than SMs: two CTAs per SM, values in L2
+    net = synth_net(118, 186, 54, seed=118)
+    pd, qd = net.perturbed_loads(B)
+    nlp = AcopfPolar(net, pd=pd, qd=qd)
+    res = {}
+    for quota in (0, 10):
+        bt = BatchSqpTR(nlp, B, Parameters(max_iter=2, init_mu=1e5), layout=dict(handoff=quota))
+        bt.trace = []
+        bt.trace_instances = {0, 57, 199}
+        recs = []
+        orig = bt.optimizer._solve
+
+        def hook(phase, x_k, delta, E_override=None, active=None, _o=orig, _r=recs, _bt=bt):
+            out = _o(phase, x_k, delta, E_override, active)
+            info = _bt.optimizer.last_info
+            _r.append((phase, out[0].copy(), out[-1].copy(), info["ipm_iters"].copy(), _bt.optimizer.engine.last_solve_kernel))
+            return out
+
+        bt.optimizer._solve = hook
+        bt.run()
+        res[quota] = (recs, [dict(t) for t in bt.trace])
+        bt.close()
+    assert all("+handoff" not in r[4] for r in res[0][0])
+    assert any("+handoff" in r[4] for r in res[10][0]), [r[4] for r in res[10][0]]
+    for a, b in zip(res[0][0], res[10][0]):
+        assert a[0] == b[0]
+        sa, sb = np.asarray(a[2]), np.asarray(b[2])
+        assert np.array_equal(np.isin(sa, OK), np.isin(sb, OK)), (sa[~np.isin(sa, OK)], sb[~np.isin(sb, OK)])
+        assert np.abs(a[3].astype(int) - b[3].astype(int)).max() <= 4, (a[3][:8], b[3][:8])
+        ok = np.isin(sa, OK)
+        if a[0] == capi.PHASE_LP:  # strictly convex projection: one solution
+            assert np.abs(a[1][ok] - b[1][ok]).max() <= 1e-6 * max(1.0, np.abs(a[1][ok]).max())
+    for b in (0, 57, 199):
+        tr = [t for t in res[10][1] if t["b"] == b]
+        for t in tr:
+            t["b"] = None
+        s = cl.check_trace(AcopfPolar(net, pd=pd[b], qd=qd[b]), tr, oracle_every=2)
+        assert s["worst_kkt"] <= 1e-6 and s["marginal_mismatch"] <= 1, (b, s)
