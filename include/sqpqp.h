@@ -223,6 +223,11 @@ int sqpqp_acopf_setup(sqpqp_handle h, int32_t nb, int32_t ng, int32_t nl, int32_
                       const double* bal_const, int32_t nsh, const int32_t* sh_bus);
 int sqpqp_acopf_eval_update(sqpqp_handle h, const double* x, const double* lambda, const int32_t* mask, double* f, double* E,
                             double* df);
+/* f and g at a TRIAL point on the device (compute_phi with alpha > 0, sqp.jl:170-183, as called by do_step!,
+ * sqp_trust_region.jl:515-530): function values only, kept in device-side trial buffers; a following
+ * sqpqp_merit(..., E_trial = NULL, f_trial = NULL, ...) reads them in place, so neither array crosses the link.
+ * mask (nullable): instances with 0 keep a copy of their current E and f.  f / E may be NULL. */
+int sqpqp_acopf_eval_trial(sqpqp_handle h, const double* x_trial, const int32_t* mask, double* f, double* E);
 /* Line-search primitives on the current device matrices (the reference's line-search driver, sqp_line_search.jl, is not
  * compiled by the reference -- sqp.jl:226 -- these are the device quantities its merit maths needs: compute_mu_rule2!
  * :280-291, compute_alpha :303-334, compute_phi sqp.jl:170-183, compute_derivative sqp.jl:190-213 + merit.jl:13-17,

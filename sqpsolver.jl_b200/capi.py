@@ -83,7 +83,7 @@ EXPORTS = [
     "sqpqp_merit", "sqpqp_kt_residuals", "sqpqp_jac_times", "sqpqp_get_csr", "sqpqp_qp_setup", "sqpqp_qp_solve",
     "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_last_solve_kernel", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
     "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read", "sqpqp_debug_set", "sqpqp_linesearch_terms", "sqpqp_acopf_setup", "sqpqp_acopf_eval_update",
-    "sqpqp_host_register", "sqpqp_host_unregister", "sqpqp_solve_ms_total",
+    "sqpqp_host_register", "sqpqp_host_unregister", "sqpqp_solve_ms_total", "sqpqp_acopf_eval_trial",
 ]
 
 
@@ -145,6 +145,7 @@ def lib():
     L.sqpqp_acopf_eval_update.argtypes = [vp, _dp, _dp, _ip, _dp, _dp, _dp]
     L.sqpqp_linesearch_terms.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
     L.sqpqp_debug_set.argtypes = [vp, C.c_int32, C.c_int32]
+    L.sqpqp_acopf_eval_trial.argtypes = [vp, _dp, _ip, _dp, _dp]
     L.sqpqp_host_register.argtypes = [vp, vp, C.c_int64]
     L.sqpqp_host_unregister.argtypes = [vp, vp]
     L.sqpqp_debug_read.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_int64]
@@ -375,8 +376,9 @@ class Engine:
         B, n, m = self.batch, self.n, self.m
         x = _f64(x).reshape(B, n)
         p = _f64(p).reshape(B, n)
-        E_trial = _f64(E_trial).reshape(B, m)
-        f_trial = np.ascontiguousarray(np.broadcast_to(np.asarray(f_trial, dtype=np.float64), (B,)))
+        # None: the trial values acopf_eval_trial left on the device
+        E_trial = _f64(E_trial).reshape(B, m) if E_trial is not None else None
+        f_trial = np.ascontiguousarray(np.broadcast_to(np.asarray(f_trial, dtype=np.float64), (B,))) if f_trial is not None else None
         mu = np.ascontiguousarray(np.broadcast_to(np.asarray(mu, dtype=np.float64), (B,)))
         frv = np.ascontiguousarray(np.broadcast_to(np.asarray(fr, dtype=np.int32), (B,))) if fr is not None else None
         out = [np.zeros(B) for _ in range(5)]
@@ -427,6 +429,17 @@ class Engine:
         f = np.zeros(B); E = np.zeros((B, m)); df = np.zeros((B, n))
         self._ck(self.L.sqpqp_acopf_eval_update(self.h, _d(x), _d(lam), _i(mk) if mk is not None else None, _d(f), _d(E), _d(df)))
         return f, E, df
+
+    def acopf_eval_trial(self, x_trial, mask=None, fetch=False):
+        """f and g at a trial point on the device (function values only), kept there for merit(..., None, None, ...);
+        fetch=True also returns (f[B], E[B,m])."""
+        B, n, m = self.batch, self.n, self.m
+        x = _f64(x_trial).reshape(B, n)
+        mk = np.ascontiguousarray(mask, dtype=np.int32) if mask is not None else None
+        f = np.zeros(B) if fetch else None
+        E = np.zeros((B, m)) if fetch else None
+        self._ck(self.L.sqpqp_acopf_eval_trial(self.h, _d(x), _i(mk) if mk is not None else None, _d(f), _d(E)))
+        return (f, E) if fetch else None
 
     def linesearch_terms(self, x, p, alpha, E_trial, mu_rows, lam):
         """Device line-search primitives (include/sqpqp.h: sqpqp_linesearch_terms); returns a dict of [batch] arrays."""

@@ -35,6 +35,7 @@ struct AcopfArgs {
     const int* mask;         // nullable: evaluate only instances with mask != 0
     double *dE, *hval, *df, *E, *f;
     int nnzJ, nnzH;
+    int fonly;               // 1: function values only (f and E at a trial point: compute_phi, sqp.jl:170-183); dE / hval / df untouched
 };
 
 __global__ void __launch_bounds__(256) k_acopf_eval(AcopfDev A, AcopfArgs G, int n, int m, int batch) {
@@ -49,11 +50,55 @@ __global__ void __launch_bounds__(256) k_acopf_eval(AcopfDev A, AcopfArgs G, int
         CtaTeam T(sh);
         const double* x = G.x + (size_t)inst * n;
         const double* lam = G.lam + (size_t)inst * m;
+        double* E = G.E + (size_t)inst * m;
+        const int tid = threadIdx.x, nt = blockDim.x;
+        if (G.fonly) {  // the same expressions as below, values only (bit-identical E and f)
+            double fo[1] = {0.0};
+            for (int k = tid; k < ng; k += nt) {
+                const double pg = x[o_pg + k], c2 = A.cost2[k], c1 = A.cost1[k];
+                fo[0] += c2 * pg * pg + c1 * pg + A.cost0[k];
+            }
+            for (int l = tid; l < nl; l += nt) {
+                const int fb = A.f_bus[l], tb = A.t_bus[l];
+                const double dth = x[o_va + fb] - x[o_va + tb];
+                E[r_angU + l] = dth;
+                E[r_angL + l] = dth;
+                const double pf = x[o_p + l], qf = x[o_q + l], pt = x[o_p + nl + l], qt = x[o_q + nl + l];
+                E[r_th + 2 * l] = pf * pf + qf * qf;
+                E[r_th + 2 * l + 1] = pt * pt + qt * qt;
+            }
+            if (tid == 0) E[r_ref] = x[o_va + A.ref_bus];
+            for (int r = tid; r < 2 * nb; r += nt) {
+                const int bus = r >> 1;
+                double acc = 0.0;
+                for (int k = A.bal_ptr[r]; k < A.bal_ptr[r + 1]; ++k) {
+                    const int kind = A.bal_kind[k];
+                    const double xv = x[A.bal_col[k]];
+                    if (kind == 0) acc += A.bal_const[k] * xv;
+                    else if (kind == 1) acc += A.gs[bus] * xv * xv;
+                    else acc -= A.bs[bus] * xv * xv;
+                }
+                E[r_bal + r] = acc;
+            }
+            for (int e = tid; e < 4 * nl; e += nt) {
+                const int l = e >> 2, k = e & 3;
+                const int fb = A.f_bus[l], tb = A.t_bus[l];
+                const int bi = (k < 2) ? fb : tb, bj = (k < 2) ? tb : fb;
+                const int var = (k == 0) ? o_p + l : (k == 1) ? o_q + l : (k == 2) ? o_p + nl + l : o_q + nl + l;
+                const double vi = x[o_vm + bi], vj = x[o_vm + bj], th = x[o_va + bi] - x[o_va + bj];
+                double sn, cs;
+                sincos(th, &sn, &cs);
+                const double C = A.oc[e] * cs + A.os[e] * sn;
+                E[r_ohm + e] = x[var] - (A.oa[e] * vi * vi + vi * vj * C);
+            }
+            T.reduce<1, false>(fo);
+            if (tid == 0) G.f[inst] = fo[0];
+            __syncthreads();
+            continue;
+        }
         double* dE = G.dE + (size_t)inst * G.nnzJ;
         double* hv = G.hval + (size_t)inst * G.nnzH;
         double* df = G.df + (size_t)inst * n;
-        double* E = G.E + (size_t)inst * m;
-        const int tid = threadIdx.x, nt = blockDim.x;
         // objective, gradient, its Hessian
         double fs[1] = {0.0};
         for (int j = tid; j < n; j += nt) df[j] = 0.0;

@@ -81,7 +81,9 @@ struct sqpqp_handle_s {
     SpmvPlan planJ{}, planT{}, planH{};
     int spmv_ctas_per_sm = 8;
     AcopfDev acopf{};       // device-side ACOPF evaluator (acopf.cuh); nb == 0: not set up
-    double* d_f = nullptr;  // [batch] objective values of the evaluator  // CSR-stream row blocks of J (normal phase), J' and H
+    double* d_f = nullptr;  // [batch] objective values of the evaluator
+    double *d_Etrial = nullptr, *d_ftrial = nullptr;  // trial-point values of sqpqp_acopf_eval_trial
+    bool trial_valid = false;  // CSR-stream row blocks of J (normal phase), J' and H
     // interleaved batch path (ilv.cuh): G instances per CTA.  ilv_G: 0 = auto, 1 = off, 2 / 4 / 8; chosen at setup
     int ilv_G = 0, ilv_threads = 0, ilv_occ = 0;
     int G = 1;                       // in effect for the current problem
@@ -401,6 +403,8 @@ static void free_problem(sqpqp_handle h) {
     h->allocs.clear();
     memset(&h->P, 0, sizeof(Prob));
     h->setup_done = h->updated = false;
+    h->d_Etrial = h->d_ftrial = nullptr;
+    h->trial_valid = false;
 }
 
 extern "C" int sqpqp_destroy(sqpqp_handle h) {
@@ -1071,6 +1075,7 @@ extern "C" int sqpqp_acopf_eval_update(sqpqp_handle h, const double* x, const do
     G.mask = mask ? upload(h, mask, B) : nullptr;
     G.dE = h->d_dE; G.hval = h->d_hval; G.df = h->d_df; G.E = h->d_E; G.f = h->d_f;
     G.nnzJ = (int)h->nnzJ_coo; G.nnzH = (int)h->nnzH_coo;
+    G.fonly = 0;
     k_acopf_eval<<<(int)(B < 65535 ? B : 65535), 256, 0, h->stream>>>(h->acopf, G, P.n, P.m, (int)B);
     h->launches++;
     P.df = h->d_df; P.E = h->d_E;
@@ -1079,6 +1084,40 @@ extern "C" int sqpqp_acopf_eval_update(sqpqp_handle h, const double* x, const do
     download(h, h->d_E, E, B * P.m);
     download(h, h->d_df, df, B * P.n);
     h->updated = true;
+    return finish(h);
+}
+
+// f and g at a TRIAL point (compute_phi with alpha > 0, sqp.jl:170-183: x + p of do_step!, sqp_trust_region.jl:515-530) on the
+// device: function values only, into trial buffers that a following sqpqp_merit(..., E_trial = NULL, f_trial = NULL) reads in
+// place.  Instances with mask == 0 get a copy of the current E and f (their trial values are not used).  f / E may be NULL
+// (nothing comes back to the host).
+extern "C" int sqpqp_acopf_eval_trial(sqpqp_handle h, const double* x_trial, const int32_t* mask, double* f, double* E) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || h->acopf.nb == 0) return fail(h, SQPQP_E_STATE, "setup / acopf_setup not called");
+    if (!x_trial) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    const size_t B = P.batch;
+    if (!h->d_Etrial) {
+        DALLOC(h->d_Etrial, B * (size_t)(P.m > 0 ? P.m : 1));
+        DALLOC(h->d_ftrial, B);
+    }
+    int rc = ensure_stage(h, B * ((size_t)P.n + P.m + 32) * sizeof(double) + B * 16 + 16384);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(h->d_Etrial, h->d_E, B * P.m * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->d_ftrial, h->d_f, B * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    AcopfArgs G;
+    G.x = upload(h, x_trial, B * P.n);
+    G.lam = nullptr;
+    G.mask = mask ? upload(h, mask, B) : nullptr;
+    G.dE = G.hval = G.df = nullptr; G.E = h->d_Etrial; G.f = h->d_ftrial;
+    G.nnzJ = (int)h->nnzJ_coo; G.nnzH = (int)h->nnzH_coo;
+    G.fonly = 1;
+    k_acopf_eval<<<(int)(B < 65535 ? B : 65535), 256, 0, h->stream>>>(h->acopf, G, P.n, P.m, (int)B);
+    h->launches++;
+    h->trial_valid = true;
+    if (f) download(h, h->d_ftrial, f, B);
+    if (E) download(h, h->d_Etrial, E, B * P.m);
     return finish(h);
 }
 
@@ -1379,7 +1418,9 @@ extern "C" int sqpqp_merit(sqpqp_handle h, const double* x, const double* p, con
                            double* q0, double* qk) {
     if (!h) return SQPQP_E_BADARG;
     if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
-    if (!x || !p || !E_trial || !f_trial || !mu) return fail(h, SQPQP_E_BADARG, "null pointer");
+    if (!x || !p || !mu) return fail(h, SQPQP_E_BADARG, "null pointer");
+    // E_trial / f_trial == NULL: the values sqpqp_acopf_eval_trial left on the device
+    if ((!E_trial || !f_trial) && !h->trial_valid) return fail(h, SQPQP_E_BADARG, "null trial values without a preceding sqpqp_acopf_eval_trial");
     DeviceGuard g(h->device);
     Prob& P = h->P;
     const size_t B = P.batch;
@@ -1388,8 +1429,8 @@ extern "C" int sqpqp_merit(sqpqp_handle h, const double* x, const double* p, con
     MeritArgs A;
     A.x = upload(h, x, B * P.n);
     A.p = upload(h, p, B * P.n);
-    A.Etrial = upload(h, E_trial, B * P.m);
-    A.ftrial = upload(h, f_trial, B);
+    A.Etrial = E_trial ? upload(h, E_trial, B * P.m) : h->d_Etrial;
+    A.ftrial = f_trial ? upload(h, f_trial, B) : h->d_ftrial;
     A.mu = upload(h, mu, B);
     A.fr = fr ? upload(h, fr, B) : nullptr;
     double* out;  // 5 x B results in the (zeroed) N_TMP workspace of instance 0.. (batch*Ne >= 5*batch only if Ne>=5)

@@ -81,6 +81,9 @@ class BatchSqpTR:
         if B * max(n, m) >= (1 << 16):
             self.optimizer.engine.register_host(self.x, self.p, self.lam, self.mult_x_L, self.mult_x_U, self.df, self.E,
                                                 self.dE, self.h_val)
+            # ... and owns ONE set of solve results (every consumer below copies what it keeps before the next solve)
+            self.optimizer.engine.reuse_outputs = True
+            self.optimizer.engine.register_outputs = True
         # f, grad f, g and the J / H COO values evaluated on the device (csrc/acopf.cuh) instead of by the
         # host callbacks -- only x and lambda go up, only f, E, grad f come back
         self.device_evaluator = bool(device_evaluator)
@@ -271,14 +274,22 @@ class BatchSqpTR:
         idx = np.nonzero(step)[0]
         t0 = time.perf_counter()
         xt = self.x + self.p
-        f_t = self.f.copy()
-        E_t = self.E.copy()
-        f_t[idx] = np.atleast_1d(pr.eval_f(xt[idx]))
-        Et = np.empty((idx.size, pr.m)); self._eval_g(xt[idx], Et, idx); E_t[idx] = Et
-        self.timers["callbacks"] += time.perf_counter() - t0
-        t0 = time.perf_counter()
-        mer = eng.merit(self.x, self.p, E_t, f_t, self.mu, self.feasibility_restoration.astype(np.int32))
-        self.timers["device"] += time.perf_counter() - t0
+        if self.device_evaluator and not opt.use_soc:
+            # compute_phi(x, 1, p) (sqp.jl:170-183): f and g at the trial point evaluated on the device and left there for the
+            # merit call -- neither array crosses the link
+            eng.acopf_eval_trial(xt, step.astype(np.int32))
+            mer = eng.merit(self.x, self.p, None, None, self.mu, self.feasibility_restoration.astype(np.int32))
+            self.timers["device"] += time.perf_counter() - t0
+            E_t = None
+        else:
+            f_t = self.f.copy()
+            E_t = self.E.copy()
+            f_t[idx] = np.atleast_1d(pr.eval_f(xt[idx]))
+            Et = np.empty((idx.size, pr.m)); self._eval_g(xt[idx], Et, idx); E_t[idx] = Et
+            self.timers["callbacks"] += time.perf_counter() - t0
+            t0 = time.perf_counter()
+            mer = eng.merit(self.x, self.p, E_t, f_t, self.mu, self.feasibility_restoration.astype(np.int32))
+            self.timers["device"] += time.perf_counter() - t0
         soc_need = np.zeros(B, bool)
         ared = np.zeros(B); q0 = mer["q0"]
         for b in idx:

@@ -549,6 +549,22 @@ def test_device_acopf_evaluator_matches_host_callbacks(engine):
         assert np.array_equal(engine.get_csr(0, 0)[2], va0_before)
         Er2 = np.zeros((B, nlp.m)); nlp.eval_g(x2, Er2)
         assert np.abs(E2[1] - Er2[1]).max() <= 1e-13 * max(1.0, np.abs(Er2).max())
+        # trial-point evaluation (function values only): the values of the full evaluation for the masked instances, the
+        # current values for the others; merit with E_trial = f_trial = None reads them on the device
+        f3, E3, _ = engine.acopf_eval_update(x2, lam)             # current point = x2 for every instance
+        xt = x2 + 0.01 * rng.standard_normal(x2.shape)
+        ft, Et = engine.acopf_eval_trial(xt, mask=np.array([1, 0, 1]), fetch=True)
+        ff, Ef, _ = engine.acopf_eval_update(xt, lam)
+        # (the compiler may contract the two code paths into different fused multiply-adds: equal to the last ulps, not bit for bit)
+        assert np.abs(Et[[0, 2]] - Ef[[0, 2]]).max() <= 1e-14 * max(1.0, np.abs(Ef).max())
+        assert np.abs(ft[[0, 2]] - ff[[0, 2]]).max() <= 1e-14 * np.abs(ff).max()
+        assert np.array_equal(Et[1], E3[1]) and ft[1] == f3[1]
+        engine.acopf_eval_update(x2, lam)
+        engine.acopf_eval_trial(xt, mask=np.array([1, 0, 1]))
+        p = xt - x2
+        m_dev = engine.merit(x2, p, None, None, np.full(B, 10.0))
+        m_host = engine.merit(x2, p, Et, ft, np.full(B, 10.0))
+        assert all(np.array_equal(m_dev[k], m_host[k]) for k in m_dev)
 
 
 def test_batched_sqp_with_device_evaluator_matches_host_evaluator(built_lib):
