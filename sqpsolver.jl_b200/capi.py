@@ -90,16 +90,34 @@ EXPORTS = [
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/sqpqp.cu for sm_100a with nvcc (cross-compiles without a GPU).
     SQPQP_PROF=1 in the environment adds the in-kernel phase profile (development builds only)."""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h"))] + [HEADER]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+    import fcntl
+
+    def stale():
+        srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".hpp", ".h"))] + [HEADER]
+        return not (os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs))
+
+    if not force and not stale():
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-DSQPQP_PROF"] if PROF_BUILD else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "sqpqp.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stderr)
+    # several ranks of one node may get here at once (torchrun): one compiles, the others wait on the lock and find the
+    # library fresh; the compiler writes a temporary file that is renamed into place, so a reader never maps a partial .so
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or stale():
+                nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+                tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+                cmd = ([nvcc] + NVCC_FLAGS + (["-DSQPQP_PROF"] if PROF_BUILD else []) + (["-Xptxas", "-v"] if verbose else [])
+                       + ["-o", tmp, os.path.join(CSRC, "sqpqp.cu")])
+                res = subprocess.run(cmd, capture_output=True, text=True)
+                if res.returncode != 0:
+                    if os.path.exists(tmp):
+                        os.remove(tmp)
+                    raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+                os.replace(tmp, LIB_PATH)
+                if verbose:
+                    sys.stderr.write(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -112,20 +112,35 @@ struct GridTeam {
 // 2^lg lanes cooperate on one row (sub-warp per row); lg is chosen on the host from the
 // row-length histogram of each matrix (short ACOPF rows -> 1..8 lanes; long rows -> 32).
 // f(row, dot) is called by lane 0 of the sub-warp.
+// Two rows per sub-warp and trip, walked together: the index -> value -> gather chains of both rows are in flight at once (a
+// single row per trip pays the three dependent L2 round trips once per row; the summation order within a row is unchanged,
+// so the results are bit-identical to the one-row loop).
 template <class Team, class F>
 __device__ __forceinline__ void csr_rows(Team& T, int nrows, int lg, const int* __restrict__ rb,
                                          const int* __restrict__ re, const int* __restrict__ col,
                                          const double* __restrict__ val, const double* __restrict__ x, F f) {
     const int L = 1 << lg, lane = T.tid() & (L - 1), sub = T.tid() >> lg, nsub = T.size() >> lg;
-    for (int r0 = 0; r0 < nrows; r0 += nsub) {
-        int r = r0 + sub;
-        double acc = 0.0;
-        if (r < nrows) {
-            int e = re[r];
-            for (int k = rb[r] + lane; k < e; k += L) acc = fma(val[k], x[col[k]], acc);
+    for (int r0 = 0; r0 < nrows; r0 += 2 * nsub) {
+        const int ra = r0 + sub, rc = ra + nsub;
+        const bool ona = ra < nrows, onc = rc < nrows;
+        int ka = ona ? rb[ra] + lane : 0, kc = onc ? rb[rc] + lane : 0;
+        const int ea = ona ? re[ra] : 0, ec = onc ? re[rc] : 0;
+        double acca = 0.0, accc = 0.0;
+        while (ka < ea || kc < ec) {
+            const bool oa = ka < ea, oc = kc < ec;
+            const int ca = col[oa ? ka : 0], cc = col[oc ? kc : 0];
+            const double va = val[oa ? ka : 0], vc = val[oc ? kc : 0];
+            const double xa = x[ca], xc = x[cc];
+            if (oa) acca = fma(va, xa, acca);
+            if (oc) accc = fma(vc, xc, accc);
+            ka += L; kc += L;
         }
-        for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (r < nrows && lane == 0) f(r, acc);
+        for (int o = L >> 1; o > 0; o >>= 1) {
+            acca += __shfl_xor_sync(0xffffffffu, acca, o);
+            accc += __shfl_xor_sync(0xffffffffu, accc, o);
+        }
+        if (ona && lane == 0) f(ra, acca);
+        if (onc && lane == 0) f(rc, accc);
     }
 }
 
@@ -140,20 +155,25 @@ __device__ __forceinline__ void csr_rows2(Team& T, int nrows, int lg, const int*
     const int L = 1 << lg, lane = T.tid() & (L - 1), sub = T.tid() >> lg, nsub = T.size() >> lg;
     for (int r0 = 0; r0 < nrows; r0 += nsub) {
         int r = r0 + sub;
+        const bool on = r < nrows;
+        // both products of the row walked together (their chains are independent)
+        int k1 = (on && use1) ? rb1[r] + lane : 0, k2 = on ? rb2[r] + lane : 0;
+        const int e1 = (on && use1) ? re1[r] : 0, e2 = on ? re2[r] : 0;
         double a1 = 0.0, a2 = 0.0;
-        if (r < nrows) {
-            if (use1) {
-                int e = re1[r];
-                for (int k = rb1[r] + lane; k < e; k += L) a1 = fma(val1[k], x1[col1[k]], a1);
-            }
-            int e2 = re2[r];
-            for (int k = rb2[r] + lane; k < e2; k += L) a2 = fma(val2[k], x2[col2[k]], a2);
+        while (k1 < e1 || k2 < e2) {
+            const bool o1 = k1 < e1, o2 = k2 < e2;
+            const int c1 = col1[o1 ? k1 : 0], c2 = col2[o2 ? k2 : 0];
+            const double v1 = val1[o1 ? k1 : 0], v2 = val2[o2 ? k2 : 0];
+            const double y1 = x1[c1], y2 = x2[c2];
+            if (o1) a1 = fma(v1, y1, a1);
+            if (o2) a2 = fma(v2, y2, a2);
+            k1 += L; k2 += L;
         }
         for (int o = L >> 1; o > 0; o >>= 1) {
             a1 += __shfl_xor_sync(0xffffffffu, a1, o);
             a2 += __shfl_xor_sync(0xffffffffu, a2, o);
         }
-        if (r < nrows && lane == 0) f(r, a1, a2);
+        if (on && lane == 0) f(r, a1, a2);
     }
 }
 
