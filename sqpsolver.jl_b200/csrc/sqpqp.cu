@@ -835,9 +835,10 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
             return (size_t)ncols * G * sizeof(double) + (size_t)52 * 53 / 2 * G * sizeof(double) <= ilv_budget;
         };
         auto tail_cap = [&](int ncols) -> int {
-            // grid team: the chain at the top of the tree (~740 columns on the 2000-bus network) becomes one dense block;
-            // 1024 columns = 4 MB packed (L2-resident), its factorisation 0.36 Gflop
-            if (grid_mode) return h->tail_override >= 0 ? h->tail_override : 1024;
+            // grid team: the chain at the top of the tree (~740 columns on the 2000-bus network) becomes one dense block.
+            // Measured on that network with the forward sweep fused into the factor phases (ms per interior-point iteration by
+            // cap): 384: 5.12, 512: 2.97, 640: 1.81, 768: 1.51, 896: 1.56, 1024: 1.69 -- 765 columns = 2.3 MB packed (L2-resident)
+            if (grid_mode) return h->tail_override >= 0 ? h->tail_override : 768;
             if (G > 1) {
                 size_t cap = ilv_budget / sizeof(double) / G;  // doubles per instance
                 if (ilv_yw_resident(ncols)) cap -= ncols;
