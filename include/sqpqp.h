@@ -108,6 +108,8 @@ typedef struct sqpqp_options {
                                 >= 3 = four 256-thread CTAs per SM (64 regs) */
     int32_t smem_kb;         /* shared-memory budget per CTA for resident work vectors; -1 = auto, 0 = none (the dense tail of
                                 the factor, its inverse diagonal and the solve scratch are always resident) */
+    double ipm_ic_growth;    /* inertia correction: factor on the diagonal shift after a failed factorisation (default 4) */
+    double ipm_ic_decay;     /* ... and divisor of the shift per interior-point iteration once it has succeeded (default 3) */
 } sqpqp_options;
 
 /* ---- lifecycle ------------------------------------------------------------------ */

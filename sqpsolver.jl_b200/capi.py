@@ -74,6 +74,7 @@ class Options(C.Structure):
         ("ipm_eps", C.c_double), ("ipm_delta0", C.c_double), ("ipm_delta_min", C.c_double), ("ipm_rho0", C.c_double),
         ("ipm_tau", C.c_double), ("ipm_mu0", C.c_double), ("ipm_mu_min", C.c_double), ("ipm_kappa_eps", C.c_double),
         ("ipm_refine", C.c_int32), ("verbose", C.c_int32), ("occupancy", C.c_int32), ("smem_kb", C.c_int32),
+        ("ipm_ic_growth", C.c_double), ("ipm_ic_decay", C.c_double),
     ]
 
 

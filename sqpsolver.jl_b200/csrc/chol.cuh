@@ -483,26 +483,20 @@ __device__ inline double dense_factor_grid(GridTeam& T, double* __restrict__ D, 
     double* dv = sm + 2 * GD_NB * GD_LD;  // [32] inverse pivots of the block
     double bad = 0.0;
     for (int j0 = 0; j0 < Tp; j0 += GD_NB) {
-        // ---- A: diagonal block, redundantly per CTA ----
+        // ---- A: diagonal block, redundantly per CTA: a packed copy is factorised by the CTA team's panel-of-4 code
+        //      (dense_factor: 2 barriers per 4 columns instead of 3 per column), then laid out square for steps B and C ----
+        double* Pk = Bk;  // 528 of its 1056 doubles
         for (int e = tid; e < GD_NB * GD_NB; e += nth) {
             const int r = e >> 5, c = e & 31;
-            A[r * GD_LD + c] = (c <= r) ? D[tri(j0 + r) + j0 + c] : 0.0;
+            if (c <= r) Pk[tri(r) + c] = D[tri(j0 + r) + j0 + c];
         }
         __syncthreads();
-        for (int c = 0; c < GD_NB; ++c) {
-            double piv = A[c * GD_LD + c];
-            if (!(piv > 0.0)) { bad = 1.0; piv = 1.0; }
-            const double inv = rsqrt(piv);
-            __syncthreads();  // every thread has read the pivot
-            if (tid >= c && tid < GD_NB) A[tid * GD_LD + c] = (tid == c ? piv : A[tid * GD_LD + c]) * inv;
-            if (tid == 0) dv[c] = inv;
-            __syncthreads();
-            for (int e = tid; e < GD_NB * GD_NB; e += nth) {
-                const int r = e >> 5, k = e & 31;
-                if (k > c && r >= k) A[r * GD_LD + k] = fma(-A[r * GD_LD + c], A[k * GD_LD + c], A[r * GD_LD + k]);
-            }
-            __syncthreads();
+        bad = fmax(bad, dense_factor(Pk, dv, GD_NB));  // ends with a barrier; dv = inverse pivots
+        for (int e = tid; e < GD_NB * GD_NB; e += nth) {
+            const int r = e >> 5, c = e & 31;
+            A[r * GD_LD + c] = (c < r) ? Pk[tri(r) + c] : (c == r ? 1.0 / dv[r] : 0.0);
         }
+        __syncthreads();
         if (blockIdx.x == 0) {
             for (int e = tid; e < GD_NB * GD_NB; e += nth) {
                 const int r = e >> 5, c = e & 31;
@@ -556,63 +550,79 @@ __device__ inline double dense_factor_grid(GridTeam& T, double* __restrict__ D, 
     return bad;  // uniform: every CTA factorised every diagonal block
 }
 
-// Tail solves of the grid team, executed by ONE CTA (the others wait at the grid barrier that follows): blocked by 32,
-// diagonal blocks solved by one warp from shared memory (registers + shuffles), off-diagonal updates by the CTA.
+// Tail solves of the grid team, executed by ONE CTA (the others wait at the grid barrier that follows): blocked by 32 and
+// LEFT-looking -- the right-hand side of a block is corrected by one mat-vec over everything solved so far (32 rows x j0
+// columns, eight lanes per row walking the packed row contiguously, all loads of a lane independent), then one warp solves
+// the 32 x 32 diagonal block from shared memory (registers + shuffles).  The right-looking variant it replaces updated every
+// remaining row after each block with four dependent 32-load chains per thread: 10 k cycles per block step against ~4 k.
 __device__ inline void dense_solve_block0(const double* __restrict__ D, const double* __restrict__ dinvT, double* yt, int Tn, int Tp, double* sm) {
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
-    double* A = sm;
-    double* yb = sm + 2 * GD_NB * GD_LD + 32;
-    for (int j0 = 0; j0 < Tp; j0 += GD_NB) {  // forward: y = L^{-1} y
+    double* A = sm;                            // [32][33] diagonal block
+    double* red = sm + GD_NB * GD_LD;          // [8][32] partial sums of the backward mat-vec / [32] of the forward one
+    for (int j0 = 0; j0 < Tp; j0 += GD_NB) {   // forward: y = L^{-1} y
         __syncthreads();
+        {   // rows j0 .. j0+31 against y[0 .. j0): thread = (row r, lane8)
+            const int r = tid >> 3, l8 = tid & 7;
+            double a0 = 0.0, a1 = 0.0;
+            if (r < GD_NB) {
+                const double* __restrict__ row = D + tri(j0 + r);
+                int k = l8;
+#pragma unroll 4
+                for (; k + 8 < j0; k += 16) { a0 = fma(row[k], yt[k], a0); a1 = fma(row[k + 8], yt[k + 8], a1); }
+                if (k < j0) a0 = fma(row[k], yt[k], a0);
+            }
+            a0 += a1;
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 4);
+            if (r < GD_NB && l8 == 0) red[r] = a0;
+        }
         for (int e = tid; e < GD_NB * GD_NB; e += nth) {
             const int r = e >> 5, c = e & 31;
             A[r * GD_LD + c] = (c <= r) ? D[tri(j0 + r) + j0 + c] : 0.0;
         }
         __syncthreads();
         if (tid < 32) {
-            double t = (j0 + lane < Tn) ? yt[j0 + lane] : 0.0;
+            double t = (j0 + lane < Tn) ? yt[j0 + lane] - red[lane] : 0.0;
             const double di = (j0 + lane < Tn) ? dinvT[j0 + lane] : 1.0;
             for (int c = 0; c < GD_NB; ++c) {
                 const double yc = __shfl_sync(0xffffffffu, t * di, c);
                 if (lane == c) t = yc;
                 else if (lane > c) t = fma(-A[lane * GD_LD + c], yc, t);
             }
-            yb[lane] = t;
             if (j0 + lane < Tn) yt[j0 + lane] = t;
-        }
-        __syncthreads();
-        for (int i = j0 + GD_NB + tid; i < Tn; i += nth) {
-            const double* __restrict__ row = D + tri(i) + j0;
-            double acc = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < GD_NB; ++c) acc = fma(row[c], yb[c], acc);
-            yt[i] -= acc;
         }
     }
     for (int j0 = Tp - GD_NB; j0 >= 0; j0 -= GD_NB) {  // backward: x = L^{-T} y
         __syncthreads();
+        {   // columns j0 .. j0+31 against x[j0+32 .. Tn): thread = (row group g, column c), rows i = j0 + 32 + g, + 8, ...
+            const int g = tid >> 5, c = tid & 31, ng = nth >> 5;
+            double a0 = 0.0, a1 = 0.0;
+            int i = j0 + GD_NB + g;
+#pragma unroll 4
+            for (; i + ng < Tn; i += 2 * ng) {
+                a0 = fma(D[tri(i) + j0 + c], yt[i], a0);
+                a1 = fma(D[tri(i + ng) + j0 + c], yt[i + ng], a1);
+            }
+            if (i < Tn) a0 = fma(D[tri(i) + j0 + c], yt[i], a0);
+            red[g * 32 + c] = a0 + a1;
+        }
         for (int e = tid; e < GD_NB * GD_NB; e += nth) {
             const int r = e >> 5, c = e & 31;
             A[r * GD_LD + c] = (c <= r) ? D[tri(j0 + r) + j0 + c] : 0.0;
         }
         __syncthreads();
         if (tid < 32) {
-            double t = (j0 + lane < Tn) ? yt[j0 + lane] : 0.0;
+            double s = 0.0;
+            for (int g = 0; g < (nth >> 5); ++g) s += red[g * 32 + lane];
+            double t = (j0 + lane < Tn) ? yt[j0 + lane] - s : 0.0;
             const double di = (j0 + lane < Tn) ? dinvT[j0 + lane] : 1.0;
             for (int c = GD_NB - 1; c >= 0; --c) {
                 const double xc = __shfl_sync(0xffffffffu, t * di, c);
                 if (lane == c) t = xc;
                 else if (lane < c) t = fma(-A[c * GD_LD + lane], xc, t);
             }
-            yb[lane] = t;
             if (j0 + lane < Tn) yt[j0 + lane] = t;
-        }
-        __syncthreads();
-        for (int k = tid; k < j0; k += nth) {  // y_k -= sum_c L[j0 + c][k] x_c   (coalesced over k)
-            double acc = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < GD_NB; ++c) acc = fma(D[tri(j0 + c) + k], yb[c], acc);
-            yt[k] -= acc;
         }
     }
     __syncthreads();

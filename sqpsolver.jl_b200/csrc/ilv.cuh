@@ -794,7 +794,7 @@ __device__ void ilv_solve_group(IlvTeam<G>& T, const Prob& P, const sqpqp_option
                         ++tries;
                         if (ok) need = false;
                         else {
-                            rho_p = fmax(fmax(4.0 * rho_p, rho_last > 0.0 ? rho_last / 3.0 : 1e-4), 1e-6);
+                            rho_p = fmax(fmax(o.ipm_ic_growth * rho_p, rho_last > 0.0 ? rho_last / o.ipm_ic_decay : 1e-4), 1e-6);
                             if (rho_p > 1e8 || tries >= 30) { need = false; live = false; failed = true; almost = false; }
                         }
                     }
@@ -854,7 +854,7 @@ __device__ void ilv_solve_group(IlvTeam<G>& T, const Prob& P, const sqpqp_option
                 sig_prev = sigma_mu;
                 del_prev = delta;
                 delta = fmax(o.ipm_delta_min, delta * 0.3);
-                if (rho_p > o.ipm_rho0) rho_p = fmax(o.ipm_rho0, rho_p / 3.0);
+                if (rho_p > o.ipm_rho0) rho_p = fmax(o.ipm_rho0, rho_p / o.ipm_ic_decay);
                 iters = it + 1;
             }
             ++it;

@@ -329,7 +329,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
             // regularisation shortens the Newton steps, the shift decays, fails and overshoots again -- the six slowest
             // recorded subproblems need 228 iterations / 330 factorisations in total with 4 against 504 / 712 with 10
             // (profiles/r01_tuning.md section 6).
-            if (!fact_ok) rho_p = fmax(fmax(4.0 * rho_p, rho_last > 0.0 ? rho_last / 3.0 : 1e-4), 1e-6);
+            if (!fact_ok) rho_p = fmax(fmax(o.ipm_ic_growth * rho_p, rho_last > 0.0 ? rho_last / o.ipm_ic_decay : 1e-4), 1e-6);
             if (rho_p > 1e8) break;
         }
         if (!fact_ok) { out.almost = false; capped = false; break; }
@@ -378,7 +378,7 @@ __device__ IpmOut ipm_run(Team& T, const Inst& I, const CholDev& C, const CholWo
         sig_prev = sigma_mu;
         del_prev = delta;
         delta = fmax(o.ipm_delta_min, delta * 0.3);
-        if (rho_p > o.ipm_rho0) rho_p = fmax(o.ipm_rho0, rho_p / 3.0);
+        if (rho_p > o.ipm_rho0) rho_p = fmax(o.ipm_rho0, rho_p / o.ipm_ic_decay);
         out.iters = it + 1;
         if (handoff_k > 0 && it + 1 >= handoff_k && it + 1 < o.ipm_max_iter) {
             // iteration quota of the throughput launch used up: the loop state goes to global memory (the vectors are there

@@ -346,6 +346,7 @@ extern "C" void sqpqp_default_options(sqpqp_options* o) {
     o->max_iter = 6000; o->check_every = 25; o->ruiz_iters = 15; o->cg_max = 300; o->eig_iters = 60;
     o->polish_outer = 20; o->polish_cg_max = 3000;
     o->warm_start = 1; o->team = 0; o->threads = 0; o->smem_kb = -1; o->occupancy = 0;
+    o->ipm_ic_growth = 4.0; o->ipm_ic_decay = 3.0;
     o->method = 0; o->ipm_max_iter = 200; o->fallback_max_iter = 1500; o->ipm_eps = 1e-9; o->ipm_delta0 = 1e-6; o->ipm_delta_min = 1e-8;
     o->ipm_rho0 = 1e-8; o->ipm_tau = 0.995; o->ipm_mu0 = 1.0; o->ipm_mu_min = 1e-14; o->ipm_kappa_eps = 10.0; o->ipm_refine = 0; o->verbose = 0;
 }

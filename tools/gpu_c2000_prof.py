@@ -20,7 +20,7 @@ def hook(phase, x_k, delta, E_override=None, active=None):
     pr = eng.prof_read().astype(np.float64)[:15]
     info = d.batch.optimizer.last_info[0]
     it = max(1, int(info["ipm_iters"]))
-    nb = 296.0  # cooperative CTAs (2 x 148)
+    nb = 148.0  # cooperative CTAs (one 256-thread CTA per SM: 255 registers)
     print(f"phase {phase} {eng.last_solve_ms:7.1f} ms ipm {it} nfact {int(info['chol_factorizations'])}  kcycles/iteration (per CTA): "
           + "  ".join(f"{s}:{v / nb / it / 1e3:6.1f}" for s, v in zip(SEG, pr) if v > 0) + f"  total {pr.sum() / nb / it / 1e3:.0f}", flush=True)
     return r

@@ -13,7 +13,7 @@ B = int(sys.argv[1]); rounds = int(sys.argv[2])
 capi.build()
 net = synth_net(118, 186, 54, 118)
 pd, qd = net.perturbed_loads(B)
-cfgs = [("default", None, 0, None), ("no handoff", None, 0, dict(handoff=0)), ("handoff 32", None, 0, dict(handoff=32)), ("handoff 40", None, 0, dict(handoff=40)), ("handoff 56", None, 0, dict(handoff=56)), ("handoff 64", None, 0, dict(handoff=64)), ("default unfused", None, 0, dict(fuse=0)), ("occ1 slot lists", dict(occupancy=1), 1, None), ("occ1 ring", dict(occupancy=1), 2, None)]
+cfgs = [("default", None, 0, None), ("tail 64", None, 0, dict(tail=64)), ("tail 80", None, 0, dict(tail=80)), ("tail 112", None, 0, dict(tail=112)), ("tail 128", None, 0, dict(tail=128)), ("no handoff", None, 0, dict(handoff=0)), ("handoff 32", None, 0, dict(handoff=32)), ("handoff 40", None, 0, dict(handoff=40)), ("handoff 56", None, 0, dict(handoff=56)), ("handoff 64", None, 0, dict(handoff=64)), ("default unfused", None, 0, dict(fuse=0)), ("occ1 slot lists", dict(occupancy=1), 1, None), ("occ1 ring", dict(occupancy=1), 2, None)]
 if len(sys.argv) > 3:
     cfgs = [c for c in cfgs if c[0] in sys.argv[3:]]
 for name, eo, ring, layout in cfgs:
