@@ -195,6 +195,13 @@ int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value); /* what 0: res
                                                                      tail of the factor in columns (-1 = auto), takes
                                                                      effect at the next setup */
 int sqpqp_debug_read(sqpqp_handle h, int32_t kind, int32_t idx, int32_t b, double* out, int64_t count);
+/* Launch order of the batched solves that follow: CTA slot k of a launch runs instance order[k] (host array, a permutation
+ * of 0..batch-1; NULL restores index order).  The hardware starts CTAs in slot order, so a caller that knows which
+ * instances are slow (e.g. from its own history) can start them first.  Results are independent of the order. */
+int sqpqp_set_launch_order(sqpqp_handle h, const int32_t* order);
+/* Development aid: raw interior-point loop states (and the per-instance flags behind them) saved by a launch that ran
+ * with an iteration quota (sqpqp_debug_set what = 8 / 9). */
+int sqpqp_debug_read_state(sqpqp_handle h, void* out, int64_t bytes);
 /* Number of slack columns S (order: for each row i > m_lin: u_i, then v_i if two-sided). */
 int sqpqp_num_slacks(sqpqp_handle h, int32_t* S);
 

@@ -85,6 +85,7 @@ EXPORTS = [
     "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_last_solve_kernel", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
     "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read", "sqpqp_debug_set", "sqpqp_linesearch_terms", "sqpqp_acopf_setup", "sqpqp_acopf_eval_update",
     "sqpqp_host_register", "sqpqp_host_unregister", "sqpqp_solve_ms_total", "sqpqp_acopf_eval_trial",
+    "sqpqp_set_launch_order", "sqpqp_debug_read_state",
 ]
 
 
@@ -168,6 +169,8 @@ def lib():
     L.sqpqp_host_register.argtypes = [vp, vp, C.c_int64]
     L.sqpqp_host_unregister.argtypes = [vp, vp]
     L.sqpqp_debug_read.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, _dp, C.c_int64]
+    L.sqpqp_set_launch_order.argtypes = [vp, _ip]
+    L.sqpqp_debug_read_state.argtypes = [vp, vp, C.c_int64]
     L.sqpqp_spmv.argtypes = [vp, C.c_int32, _dp, _dp]
     L.sqpqp_spmv_device.argtypes = [vp, C.c_int32, vp, vp]
     L.sqpqp_num_slacks.argtypes = [vp, _ip]
@@ -269,7 +272,28 @@ class Engine:
             setattr(self.opts, k, v)
         self._ck(self.L.sqpqp_set_options(self.h, C.byref(self.opts)))
 
-    def set_layout(self, G=0, threads=0, ctas_per_sm=0, tail=-1, ring=None, fuse=None, handoff=None):
+    def set_launch_order(self, order=None):
+        """CTA slot k of the following batched solves runs instance order[k] (None: index order)."""
+        if order is None:
+            self._ck(self.L.sqpqp_set_launch_order(self.h, None))
+        else:
+            o = np.ascontiguousarray(order, dtype=np.int32)
+            assert o.shape == (self.batch,)
+            self._ck(self.L.sqpqp_set_launch_order(self.h, _i(o)))
+
+    IPM_STATE_DTYPE = np.dtype([("delta", "f8"), ("rho_p", "f8"), ("rho_last", "f8"), ("mu_t", "f8"), ("alpha", "f8"), ("sig_prev", "f8"),
+                                ("del_prev", "f8"), ("rp_ref", "f8"), ("nin", "f8"), ("it", "i4"), ("nfact", "i4"), ("acc_cnt", "i4"), ("pad", "i4")])
+
+    def read_ipm_state(self):
+        """(development) loop states saved by a launch with an iteration quota, and the per-instance flags (3 = stopped by the quota)."""
+        B = self.batch
+        raw = np.zeros(B * (self.IPM_STATE_DTYPE.itemsize + 4), dtype=np.uint8)
+        self._ck(self.L.sqpqp_debug_read_state(self.h, raw.ctypes.data_as(C.c_void_p), raw.nbytes))
+        st = raw[:B * self.IPM_STATE_DTYPE.itemsize].view(self.IPM_STATE_DTYPE).copy()
+        fl = raw[B * self.IPM_STATE_DTYPE.itemsize:].view(np.int32).copy()
+        return st, fl
+
+    def set_layout(self, G=0, threads=0, ctas_per_sm=0, tail=-1, ring=None, fuse=None, handoff=None, handoff_mode=None):
         """Layout of the batched interior-point launch, effective at the next setup_nlp: G instances interleaved per CTA
         (0 = auto, 1 = one CTA per instance, 2 / 4 / 8), its CTA size (0 = auto, 256 / 512 / 1024), CTAs per SM
         (0 = auto) and the cap of the dense tail of the factor in columns (-1 = auto).  ring (effective at the next solve):
@@ -281,6 +305,8 @@ class Engine:
             self._ck(self.L.sqpqp_debug_set(self.h, 6, int(ring)))
         if handoff is not None:  # iteration quota before the resident launch takes an instance over (-1 auto, 0 off)
             self._ck(self.L.sqpqp_debug_set(self.h, 8, int(handoff)))
+        if handoff_mode is not None:  # 0 resident launch takes the stragglers, 1 second throughput launch longest-predicted-first, 2 stop, 3 second launch in index order
+            self._ck(self.L.sqpqp_debug_set(self.h, 9, int(handoff_mode)))
         if fuse is not None:  # (next setup_nlp) 0: forward sweep of the Newton solve as its own level-scheduled pass
             self._ck(self.L.sqpqp_debug_set(self.h, 7, int(fuse)))
 

@@ -27,6 +27,7 @@ struct DevOpts {
     int handoff_k;   // > 0: an interior-point solve that has not finished after this many iterations saves its state and is
                      //      flagged 3 for the resident launch that follows (stragglers finish there at lower latency)
     int resume;      // 1: this launch continues the instances flagged 3 and skips all others
+    const int* order;  // nullable: CTA slot k of the launch runs instance order[k] (longest-first order of a resumed batch)
 };
 
 // A work-vector slot resolved to its address at the point of use, from kernel parameters (constant
@@ -846,7 +847,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_solve_cta(const __grid_constant_
     __shared__ double sh[2 * SQPQP_MAX_RED * 32];
     __shared__ unsigned long long rbar[RING_S];  // mbarriers of the index-program ring (chol.cuh)
     extern __shared__ double dsm[];
-    for (int inst = blockIdx.x; inst < P.batch; inst += gridDim.x) {
+    for (int slot = blockIdx.x; slot < P.batch; slot += gridDim.x) {
+        const int inst = O.order ? O.order[slot] : slot;
         if (P.active && !P.active[inst]) continue;
         CtaTeam T(sh);
         solve_instance<MODE, CtaTeam, (MINB == 1 && MODE == 1)>(T, P, O.o, inst, phase, &pl, dsm, rbar, MODE == 1 ? O.handoff_k : 0,

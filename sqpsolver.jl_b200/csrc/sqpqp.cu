@@ -62,6 +62,14 @@ struct sqpqp_handle_s {
     int handoff = -1;                     // what = 8: iteration quota of the throughput launch before an instance is handed to the
                                           // resident launch; -1 auto (40 when num_sms < batch <= 2 num_sms and the ring fits), 0 off
     int fuse_fwd = 1;                     // what = 7: 0 keeps the forward sweep out of the factor program (slot lists); at setup
+    // what = 9: what follows the quota of the throughput launch.  0: the resident ring launch continues the stragglers
+    // (shards of one wave); 1: a second THROUGHPUT launch continues every unfinished instance LONGEST-FIRST, in the order
+    // k_rank_unfinished predicts from the saved interior-point state (multi-wave shards: the tail of a launch is its
+    // stragglers, and which instances they are shows in the first iterations); 2: nothing (development: state read-back);
+    // 3: second throughput launch in index order (control of 1)
+    int handoff_mode = 0;
+    int* d_order = nullptr;               // [batch] launch order of the second stage / of sqpqp_set_launch_order
+    bool order_user = false;              // d_order was set by the caller and applies to the next launches
     int ring_enable = 1;                  // sqpqp_debug_set what = 5: 0 keeps the slot lists (no ring programs are built); at setup
     bool last_ring = false;
     // caller buffers page-locked with sqpqp_host_register: copied to / from the device directly, without the pinned staging hop
@@ -557,7 +565,39 @@ extern "C" int sqpqp_debug_set(sqpqp_handle h, int32_t what, int32_t value) {  /
     if (what == 5) h->ring_enable = value != 0;
     if (what == 7) h->fuse_fwd = value != 0;
     if (what == 8) h->handoff = value;
+    if (what == 9 && value >= 0 && value <= 3) h->handoff_mode = value;
     if (what == 6 && value >= 0 && value <= 2) h->ring_mode = value;
+    return 0;
+}
+
+// Launch order of the batched solve: CTA slot k runs instance order[k] (a permutation of 0..batch-1; NULL = index order).
+extern "C" int sqpqp_set_launch_order(sqpqp_handle h, const int32_t* order) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    DeviceGuard g(h->device);
+    if (!order) { h->order_user = false; return 0; }
+    const size_t B = h->P.batch;
+    std::vector<char> seen(B, 0);
+    for (size_t k = 0; k < B; ++k) {
+        if (order[k] < 0 || (size_t)order[k] >= B || seen[order[k]]) return fail(h, SQPQP_E_BADARG, "launch order is not a permutation of the batch");
+        seen[order[k]] = 1;
+    }
+    CUDA_OK(cudaMemcpyAsync(h->d_order, order, B * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->order_user = true;
+    return 0;
+}
+
+// Development aid: the interior-point loop states saved by a launch with an iteration quota (sizeof(IpmState) bytes each).
+extern "C" int sqpqp_debug_read_state(sqpqp_handle h, void* out, int64_t bytes) {
+    if (!h || !out) return SQPQP_E_BADARG;
+    if (!h->setup_done) return fail(h, SQPQP_E_STATE, "setup not called");
+    DeviceGuard g(h->device);
+    const size_t need = (size_t)h->P.batch * (sizeof(IpmState) + sizeof(int));
+    if ((size_t)bytes < need) return fail(h, SQPQP_E_BADARG, "state buffer too small");
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaMemcpy(out, h->P.ipm_state, (size_t)h->P.batch * sizeof(IpmState), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy((char*)out + (size_t)h->P.batch * sizeof(IpmState), h->P.fb_flag, (size_t)h->P.batch * sizeof(int), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -737,6 +777,8 @@ extern "C" int sqpqp_setup_nlp(sqpqp_handle h, int32_t batch, int32_t n, int32_t
     DALLOC(P.o_info, B);
     DALLOC(P.fb_flag, B);
     DALLOC(P.ipm_state, B);
+    DALLOC(h->d_order, B);
+    h->order_user = false;
     DALLOC(h->d_dE, B * (size_t)nnz_j); DALLOC(h->d_hval, B * (size_t)nnz_h); DALLOC(h->d_df, B * n); DALLOC(h->d_E, B * (m > 0 ? m : 1));
     DALLOC(h->d_xk, B * n); DALLOC(h->d_delta, B); DALLOC(h->d_Eov, B * (m > 0 ? m : 1)); DALLOC(h->d_active, B);
     const size_t nb = bounds_per_instance ? B : 1;
@@ -1191,6 +1233,37 @@ static int pick_threads(sqpqp_handle h, int phase) {
     return t;
 }
 
+// Launch order of the second stage of a two-stage batched solve: the instances the iteration quota stopped (flag 3), by
+// descending predicted remaining work; finished instances (their CTAs return at once) behind them.  Rank sort: B is a few
+// thousand at most, every thread counts the keys ahead of its own through shared-memory tiles.
+__device__ __forceinline__ double unfinished_key(const IpmState& s, int flag, double rho0) {
+    if (flag != 3) return -1.0;
+    // failed factorisations so far (inertia corrections: the subproblem is indefinite where the iterates are), a shift still
+    // above its floor, and how far the barrier parameter still has to fall
+    const double fails = (double)(s.nfact - s.it);
+    const double mu = log10(fmax(s.mu_t, 1e-12)) + 12.0;
+    return 1.0 + 100.0 * fails + (s.rho_p > rho0 ? 50.0 : 0.0) + 2.0 * mu;
+}
+__global__ void __launch_bounds__(256) k_rank_unfinished(const IpmState* __restrict__ st, const int* __restrict__ flag, int* __restrict__ order,
+                                                         int B, double rho0) {
+    __shared__ double tile[256];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double ki = i < B ? unfinished_key(st[i], flag[i], rho0) : 0.0;
+    int rank = 0;
+    for (int j0 = 0; j0 < B; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        tile[threadIdx.x] = j < B ? unfinished_key(st[j], flag[j], rho0) : -2.0;
+        __syncthreads();
+        const int lim = min(256, B - j0);
+        for (int t = 0; t < lim; ++t) {
+            const double kj = tile[t];
+            rank += (kj > ki || (kj == ki && j0 + t < i)) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+    if (i < B) order[rank] = i;
+}
+
 static int launch_solve(sqpqp_handle h, int phase) {
     Prob& P = h->P;
     const size_t B = P.batch;
@@ -1255,19 +1328,19 @@ static int launch_solve(sqpqp_handle h, int phase) {
         // interior-point launch, then the ADMM launch for the instances it flagged (a no-op for the others); with
         // options.method == 1 only the ADMM launch (all instances), with method == 2 only the interior-point one
         const int cfg = (occ >= 3 && threads <= 256) ? 4 : (occ >= 2 ? 2 : 1);
-        auto launch = [&](int mode) {
+        auto launch = [&](int mode, const DevOpts& OO) {
             if (cfg == 4) {
-                if (mode == 1) k_solve_cta<256, 4, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
-                else k_solve_cta<256, 4, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+                if (mode == 1) k_solve_cta<256, 4, 1><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
+                else k_solve_cta<256, 4, 2><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
             } else if (cfg == 2 && threads <= 384) {  // 85 registers per thread instead of 64
-                if (mode == 1) k_solve_cta<384, 2, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
-                else k_solve_cta<384, 2, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+                if (mode == 1) k_solve_cta<384, 2, 1><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
+                else k_solve_cta<384, 2, 2><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
             } else if (cfg == 2) {
-                if (mode == 1) k_solve_cta<512, 2, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
-                else k_solve_cta<512, 2, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+                if (mode == 1) k_solve_cta<512, 2, 1><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
+                else k_solve_cta<512, 2, 2><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
             } else {
-                if (mode == 1) k_solve_cta<512, 1, 1><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
-                else k_solve_cta<512, 1, 2><<<grid, threads, dyn, h->stream>>>(P, O, phase, pl);
+                if (mode == 1) k_solve_cta<512, 1, 1><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
+                else k_solve_cta<512, 1, 2><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
             }
             h->launches++;
         };
@@ -1280,7 +1353,9 @@ static int launch_solve(sqpqp_handle h, int phase) {
         Placement pl2;
         size_t dyn2 = 0;
         int quota = 0;
-        if (ipm && cfg >= 2 && !(h->G > 1) && CD.ring_ok && h->ring_mode != 1 && h->opts.method != 1 && h->handoff != 0) {
+        const int hmode = h->handoff_mode;
+        if (ipm && hmode != 0 && !(h->G > 1) && h->opts.method != 1 && h->handoff > 0 && h->handoff < h->opts.ipm_max_iter) quota = h->handoff;
+        if (hmode == 0 && ipm && cfg >= 2 && !(h->G > 1) && CD.ring_ok && h->ring_mode != 1 && h->opts.method != 1 && h->handoff != 0) {
             place_arrays(P, phase, (size_t)h->max_dyn_smem, true, true, &pl2, true);
             if (pl2.ring >= 0 && pl2.lval >= 0 && pl2.dinv >= 0 && pl2.yw >= 0 && (CD.T == 0 || pl2.dtail >= 0)) {
                 // measured (profiles/r02_tuning.md section 7): a gain only while the whole shard is co-resident in the throughput
@@ -1293,28 +1368,39 @@ static int launch_solve(sqpqp_handle h, int phase) {
             }
         }
         O.handoff_k = quota;
+        O.order = (h->order_user && hmode != 1) ? h->d_order : nullptr;
         const bool use_ilv = ipm && h->G > 1 && (phase == SQPQP_PHASE_FR ? h->has_ilv_fr : h->has_ilv);
         if (use_ilv) {  // G instances interleaved per CTA (ilv.cuh); flags what it cannot finish for the ADMM launch below
             CUDA_OK(launch_ilv(h, O, phase, phase == SQPQP_PHASE_FR ? h->ilv_fr : h->ilv, phase == SQPQP_PHASE_FR ? h->ilv_fr_dyn : h->ilv_dyn));
             h->launches++;
             h->last_kernel = "k_solve_ilv<" + std::to_string(h->G) + "," + std::to_string(h->ilv_nt) + "," + std::to_string(h->ilv_minb) + ">";
         } else if (ipm) {
-            launch(1);
-            if (quota > 0) {
+            launch(1, O);
+            if (quota > 0 && hmode == 0) {
                 DevOpts O2 = O;
                 O2.handoff_k = 0; O2.resume = 1;
                 int t2 = pick_threads(h, phase);
                 if (t2 > 512) t2 = 512;
                 k_solve_cta<512, 1, 1><<<grid, t2, dyn2, h->stream>>>(P, O2, phase, pl2);
                 h->launches++;
+            } else if (quota > 0 && (hmode == 1 || hmode == 3)) {
+                // second stage in the same launch configuration: every instance the quota stopped, longest predicted first
+                DevOpts O2 = O;
+                O2.handoff_k = 0; O2.resume = 1; O2.order = nullptr;
+                if (hmode == 1 && B <= 16384) {
+                    k_rank_unfinished<<<(unsigned)((B + 255) / 256), 256, 0, h->stream>>>(P.ipm_state, P.fb_flag, h->d_order, (int)B, h->opts.ipm_rho0);
+                    h->launches++;
+                    O2.order = h->d_order;
+                }
+                launch(1, O2);
             }
             h->last_kernel = cfg == 4 ? "k_solve_cta<256,4,1>" : (cfg == 2 ? (threads <= 384 ? "k_solve_cta<384,2,1>" : "k_solve_cta<512,2,1>") : (pl.ring >= 0 ? "k_solve_cta<512,1,1>+ring" : "k_solve_cta<512,1,1>"));
-            if (quota > 0) h->last_kernel += "+handoff";
+            if (quota > 0) h->last_kernel += hmode == 0 ? "+handoff" : (hmode == 1 ? "+resume(ranked)" : (hmode == 3 ? "+resume" : "+stop"));
         } else {  // no factorisation available: every instance is "flagged" (non-zero) for the ADMM launch
             h->last_kernel = "k_solve_cta<..,2> (ADMM)";
             CUDA_OK(cudaMemsetAsync(P.fb_flag, 1, B * sizeof(int), h->stream));
         }
-        if (h->opts.method != 2) launch(2);
+        if (h->opts.method != 2) launch(2, O);
         h->launches--;  // counted below
     }
     h->launches++;

@@ -42,6 +42,8 @@ class Opts:
     sigma_rule = 0.0   # > 0: barrier target = sigma * current average complementarity, every iteration
     kappa_mu = 0.2     # linear / superlinear decrease of the barrier parameter (Ipopt: 0.2, 1.5)
     theta_mu = 1.5
+    refine = True      # one step of iterative refinement of the Newton solve against the assembled K
+    factor = None      # optional callable K -> (solver with .solve(rhs), ok): e.g. a modified factorisation
 
 
 class _SymLU:
@@ -143,7 +145,9 @@ def ipm_solve(P, q, J, rl, ru, xl, xu, o: Opts = Opts()):
         w_box = np.where(eqx, 1.0 / delta, np.where(xu_f, z_xu / d_xu, 0.0) + np.where(xl_f, z_xl / d_xl, 0.0))
         while True:
             K = (Ps + sp.diags(rho_p + w_box) + JsT @ sp.diags(w_row) @ Js).tocsc()
-            if o.use_sym:
+            if o.factor is not None:
+                lu, ok = o.factor(K)
+            elif o.use_sym:
                 lu = _SymLU(Ps, Js, rho_p + w_box, w_row); ok = lu.ok
             else:
                 lu, ok = chol_solve(K, None)
@@ -164,7 +168,8 @@ def ipm_solve(P, q, J, rl, ru, xl, xu, o: Opts = Opts()):
             t_box = np.where(eqx, r_eqx / delta, np.where(xu_f, (rc_xu + z_xu * r_xu) / d_xu, 0.0) - np.where(xl_f, (rc_xl + z_xl * r_xl) / d_xl, 0.0))
             rhs = -r_x - JsT @ t_row - t_box
             dx = lu.solve(rhs)
-            dx += lu.solve(rhs - K @ dx)
+            if o.refine:
+                dx += lu.solve(rhs - K @ dx)
             Jdx = Js @ dx
             dz_ru = np.where(ru_f, (rc_ru + z_ru * (r_ru + Jdx)) / d_ru, 0.0)
             dz_rl = np.where(rl_f, (rc_rl + z_rl * (r_rl - Jdx)) / d_rl, 0.0)

@@ -135,3 +135,60 @@ def test_handoff_to_the_resident_launch_matches_the_uninterrupted_solve(built_li
             t["b"] = None
         s = cl.check_trace(AcopfPolar(net, pd=pd[b], qd=qd[b]), tr, oracle_every=2)
         assert s["worst_kkt"] <= 1e-6 and s["marginal_mismatch"] <= 1, (b, s)
+
+
+def test_launch_order_and_two_stage_launch_do_not_change_the_results(built_lib):
+    """sqpqp_set_launch_order permutes which CTA slot runs which instance; the two-stage launch (iteration quota, loop state
+    saved, every unfinished instance resumed by a second launch of the SAME kernel, in index order or in the order the
+    device ranks from the saved states) interrupts every solve once.  Neither may change a bit of the results: the same code
+    runs every instance on the same data (profiles/r02_tuning.md section 8: an oracle order is worth 15-24 % of a multi-wave
+    launch, but nothing known before or early in a solve predicts its length)."""
+    B = 320  # more than 2 x 148 resident CTAs: the order matters for who starts first
+    net = synth_net(118, 186, 54, seed=118)
+    pd, qd = net.perturbed_loads(B)
+    nlp = AcopfPolar(net, pd=pd, qd=qd)
+    bt = BatchSqpTR(nlp, B, Parameters(max_iter=2, init_mu=1e5))
+    eng = bt.optimizer.engine
+    recs = {}
+    orig = bt.optimizer._solve
+    state = {"n": 0}
+
+    def hook(phase, x_k, delta, E_override=None, active=None):
+        state["n"] += 1
+        if phase != capi.PHASE_QP or state["n"] < 2:
+            return orig(phase, x_k, delta, E_override, active)
+        rng = np.random.default_rng(5)
+
+        def run(tag):
+            out = orig(phase, x_k, delta, E_override, active)
+            recs[tag] = (out[0].copy(), out[1].copy(), np.asarray(out[-1]).copy(), bt.optimizer.last_info.copy(), eng.last_solve_kernel)
+
+        run("base")
+        eng.set_launch_order(rng.permutation(B))
+        run("permuted")
+        eng.set_launch_order(None)
+        for mode, tag in ((3, "two_stage"), (1, "two_stage_ranked")):
+            eng.set_layout(handoff=9, handoff_mode=mode)
+            run(tag)
+        eng.set_layout(handoff=-1, handoff_mode=0)
+        return orig(phase, x_k, delta, E_override, active)
+
+    bt.optimizer._solve = hook
+    bt.run()
+    bt.close()
+    assert set(recs) == {"base", "permuted", "two_stage", "two_stage_ranked"}
+    p0, l0, s0, i0, k0 = recs["base"]
+    assert i0["ipm_iters"].min() > 9  # every instance is interrupted by the quota of the two-stage runs
+    assert "+resume" in recs["two_stage"][4] and "ranked" in recs["two_stage_ranked"][4], (recs["two_stage"][4], recs["two_stage_ranked"][4])
+    for tag in ("permuted", "two_stage", "two_stage_ranked"):
+        p, lam, st, info, _ = recs[tag]
+        assert np.array_equal(st, s0), tag
+        assert np.array_equal(info["ipm_iters"], i0["ipm_iters"]) and np.array_equal(info["chol_factorizations"], i0["chol_factorizations"]), tag
+        assert np.array_equal(p, p0) and np.array_equal(lam, l0), (tag, np.abs(p - p0).max())
+    with pytest.raises(capi.SqpQpError):
+        eng2 = capi.Engine()
+        try:
+            _setup(eng2, AcopfPolar(case9()), batch=4)
+            eng2.set_launch_order([0, 1, 1, 3])  # not a permutation
+        finally:
+            eng2.close()
