@@ -336,6 +336,8 @@ def main():
     ap.add_argument("--layout-ctas", dest="layout_ctas", type=int, default=0)
     ap.add_argument("--layout-tail", dest="layout_tail", type=int, default=-1)
     ap.add_argument("--no-single2000", action="store_true", help="skip the single-instance 2000-bus leg (BASELINE configs[3])")
+    ap.add_argument("--sequential-phases", dest="sequential_phases", action="store_true",
+                    help="A/B: QP-phase and restoration-phase launches of a round one after the other (two calls) instead of side by side")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -376,6 +378,7 @@ def main():
 
     layout = dict(G=args.layout_G, threads=args.layout_threads, ctas_per_sm=args.layout_ctas, tail=args.layout_tail)
     sqp = BatchSqpTR(nlp, Bl, Parameters(**kw), device=local, layout=layout)
+    sqp.mixed_phases = not args.sequential_phases
     # replayed rounds are sampled UNIFORMLY over the whole solve (round 1, 1 + T/R, ...): late rounds carry the stragglers
     stride = max(1, args.sqp_max_iter // max(1, args.rounds))
     sample_rounds = {1 + k * stride for k in range(args.rounds)}
@@ -383,7 +386,13 @@ def main():
     orig_solve = sqp.optimizer._solve
 
     def solve_hook(phase, x_k, delta, E_override=None, active=None):
-        if phase in (capi.PHASE_QP, capi.PHASE_FR) and sqp.rounds in sample_rounds:
+        if phase == capi.PHASE_MIXED and sqp.rounds in sample_rounds:  # both phases of the round in one call
+            rec.append({"round": sqp.rounds, "dE": sqp.dE.copy(), "h_val": sqp.h_val.copy(), "df": sqp.df.copy(),
+                        "E": sqp.E.copy(), "x": sqp.x.copy(), "Delta": sqp.Delta.copy(),
+                        "qp": np.asarray(active[0], np.int32).copy(), "fr": np.asarray(active[1], np.int32).copy(),
+                        "lam": sqp.lam.copy(), "mxU": sqp.mult_x_U.copy(), "mxL": sqp.mult_x_L.copy(),
+                        "mu": sqp.mu.copy(), "f": sqp.f.copy()})
+        elif phase in (capi.PHASE_QP, capi.PHASE_FR) and sqp.rounds in sample_rounds:
             act = np.ones(Bl, bool) if active is None else np.asarray(active, bool)
             if rec and rec[-1].get("round") == sqp.rounds:
                 rec[-1]["fr" if phase == capi.PHASE_FR else "qp"] = act.astype(np.int32)
@@ -430,10 +439,14 @@ def main():
         if j % R == 0:
             eng.set_options(warm_start=0)  # round 1 of a solve is cold
         eng.update_nlp_device(ptr(d["dE"]), ptr(d["h_val"]), ptr(d["df"]), ptr(d["E"]))
-        if int(rec[j % R]["qp"].sum()):
-            eng.solve_tr_device(capi.PHASE_QP, ptr(d["x"]), ptr(d["Delta"]), None, ptr(d["qp"]))
-        if int(rec[j % R]["fr"].sum()):
-            eng.solve_tr_device(capi.PHASE_FR, ptr(d["x"]), ptr(d["Delta"]), None, ptr(d["fr"]))
+        nq, nf = int(rec[j % R]["qp"].sum()), int(rec[j % R]["fr"].sum())
+        if nq and nf and not args.sequential_phases:  # instances in both phases: one call, the two launches side by side
+            eng.solve_tr_mixed_device(ptr(d["x"]), ptr(d["Delta"]), ptr(d["qp"]), ptr(d["fr"]))
+        else:
+            if nq:
+                eng.solve_tr_device(capi.PHASE_QP, ptr(d["x"]), ptr(d["Delta"]), None, ptr(d["qp"]))
+            if nf:
+                eng.solve_tr_device(capi.PHASE_FR, ptr(d["x"]), ptr(d["Delta"]), None, ptr(d["fr"]))
         if j % R == 0:
             eng.set_options(warm_start=1)
 
@@ -447,10 +460,14 @@ def main():
         eng.merit(r["x"], p_zero, r["E"], r["f"], r["mu"])
         eng.kt_residuals(r["lam"], r["mxU"], r["mxL"])
         out = None
-        if int(r["qp"].sum()):
-            out = eng.solve_tr(capi.PHASE_QP, r["x"], r["Delta"], active=r["qp"])
-        if int(r["fr"].sum()):
-            out = eng.solve_tr(capi.PHASE_FR, r["x"], r["Delta"], active=r["fr"])
+        nq, nf = int(r["qp"].sum()), int(r["fr"].sum())
+        if nq and nf and not args.sequential_phases:
+            out = eng.solve_tr_mixed(r["x"], r["Delta"], r["qp"], r["fr"])
+        else:
+            if nq:
+                out = eng.solve_tr(capi.PHASE_QP, r["x"], r["Delta"], active=r["qp"])
+            if nf:
+                out = eng.solve_tr(capi.PHASE_FR, r["x"], r["Delta"], active=r["fr"])
         if j % R == 0:
             eng.set_options(warm_start=1)
         return out
@@ -595,6 +612,7 @@ def main():
             # the same full batched SQP solve with f, grad f, g, J and H values evaluated on the device (csrc/acopf.cuh,
             # SURVEY 8f rank 1) instead of by the host callbacks: only x and lambda go up per round
             sqp2 = BatchSqpTR(nlp, Bl, Parameters(**kw), device=local, device_evaluator=True)
+            sqp2.mixed_phases = not args.sequential_phases
             t0 = time.perf_counter()
             sqp2.run()
             line["full_sqp_solve_device_evaluator"] = {

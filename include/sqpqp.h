@@ -175,6 +175,18 @@ int sqpqp_solve_tr(sqpqp_handle h, int32_t phase, const double* x_k, const doubl
  * copies only the per-instance info records back. */
 int sqpqp_solve_tr_device(sqpqp_handle h, int32_t phase, const double* x_k, const double* delta,
                           const double* E_override, const int32_t* active);
+/* One SQP round of a BATCH whose instances are in different phases (compute_step!, sqp_trust_region.jl:370-380, decides per
+ * instance between sub_optimize! and sub_optimize_FR!): instances with active_qp[b] != 0 solve the QP subproblem, instances with
+ * active_fr[b] != 0 the feasibility-restoration LP, all others are skipped (outputs untouched).  The two masks must be disjoint
+ * (SQPQP_E_BADARG otherwise).  Equivalent to two sqpqp_solve_tr calls, but x_k / delta go up once, the results come back once,
+ * and the two launches run side by side on two streams instead of one after the other (a round has few instances in
+ * restoration; their launch alone leaves the GPU idle).  Blocking; outputs as for sqpqp_solve_tr. */
+int sqpqp_solve_tr_mixed(sqpqp_handle h, const double* x_k, const double* delta, const int32_t* active_qp,
+                         const int32_t* active_fr, double* p, double* lambda, double* mult_x_L, double* mult_x_U,
+                         double* slack, int32_t* moi_status, sqpqp_info* info);
+/* ... with DEVICE pointers (masks included; the caller guarantees that they are disjoint); does not block. */
+int sqpqp_solve_tr_mixed_device(sqpqp_handle h, const double* x_k, const double* delta, const int32_t* active_qp,
+                                const int32_t* active_fr);
 int sqpqp_sync(sqpqp_handle h);
 int sqpqp_device_outputs(sqpqp_handle h, double** p, double** lambda, double** mult_x_L, double** mult_x_U,
                          sqpqp_info** info);

@@ -38,6 +38,7 @@ MOI_NAMES = {
     10: "ALMOST_LOCALLY_SOLVED", 11: "ITERATION_LIMIT", 20: "NUMERICAL_ERROR",
 }
 PHASE_QP, PHASE_FR, PHASE_SOC, PHASE_LP = 0, 1, 2, 3
+PHASE_MIXED = -1  # host-side convention (QpDevice._solve): QP phase and restoration phase of one round in one call (sqpqp_solve_tr_mixed)
 
 
 class Info(C.Structure):
@@ -85,7 +86,7 @@ EXPORTS = [
     "sqpqp_launch_count", "sqpqp_last_solve_ms", "sqpqp_last_solve_kernel", "sqpqp_solve_tr_device", "sqpqp_sync", "sqpqp_device_outputs",
     "sqpqp_fetch_info", "sqpqp_chol_stats", "sqpqp_chol_layout", "sqpqp_prof_read", "sqpqp_spmv", "sqpqp_spmv_device", "sqpqp_debug_read", "sqpqp_debug_set", "sqpqp_linesearch_terms", "sqpqp_acopf_setup", "sqpqp_acopf_eval_update",
     "sqpqp_host_register", "sqpqp_host_unregister", "sqpqp_solve_ms_total", "sqpqp_acopf_eval_trial",
-    "sqpqp_set_launch_order", "sqpqp_debug_read_state",
+    "sqpqp_set_launch_order", "sqpqp_debug_read_state", "sqpqp_solve_tr_mixed", "sqpqp_solve_tr_mixed_device",
 ]
 
 
@@ -154,6 +155,8 @@ def lib():
     L.sqpqp_update_nlp_device.argtypes = [vp, vp, vp, vp, vp]
     L.sqpqp_solve_tr.argtypes = [vp, C.c_int32, _dp, _dp, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _ip, C.c_void_p]
     L.sqpqp_solve_tr_device.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
+    L.sqpqp_solve_tr_mixed.argtypes = [vp, _dp, _dp, _ip, _ip, _dp, _dp, _dp, _dp, _dp, _ip, C.c_void_p]
+    L.sqpqp_solve_tr_mixed_device.argtypes = [vp, vp, vp, vp, vp]
     L.sqpqp_sync.argtypes = [vp]
     L.sqpqp_device_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.sqpqp_fetch_info.argtypes = [vp, C.c_void_p]
@@ -342,7 +345,7 @@ class Engine:
     def update_nlp_device(self, dE_ptr, h_val_ptr, df_ptr, E_ptr):
         self._ck(self.L.sqpqp_update_nlp_device(self.h, dE_ptr, h_val_ptr, df_ptr, E_ptr))
 
-    def solve_tr(self, phase, x_k, delta, E_override=None, active=None):
+    def solve_tr(self, phase, x_k, delta, E_override=None, active=None, mixed=None):
         B, n, m, S = self.batch, self.n, self.m, self.S
         x_k = _f64(x_k).reshape(B, n)
         delta = np.ascontiguousarray(np.broadcast_to(np.asarray(delta, dtype=np.float64), (B,)))
@@ -365,9 +368,22 @@ class Engine:
                 self._out = (p, lam, mxL, mxU, slack, status, info)
                 if self.register_outputs:
                     self.register_host(p, lam, mxL, mxU, slack, status, info)
-        self._ck(self.L.sqpqp_solve_tr(self.h, phase, _d(x_k), _d(delta), _d(E_override), _i(act), _d(p), _d(lam), _d(mxL),
-                                       _d(mxU), _d(slack), _i(status), info.ctypes.data_as(C.c_void_p)))
+        if mixed is not None:
+            aq, af = (np.ascontiguousarray(a, dtype=np.int32).reshape(B) for a in mixed)
+            self._ck(self.L.sqpqp_solve_tr_mixed(self.h, _d(x_k), _d(delta), _i(aq), _i(af), _d(p), _d(lam), _d(mxL), _d(mxU),
+                                                 _d(slack), _i(status), info.ctypes.data_as(C.c_void_p)))
+        else:
+            self._ck(self.L.sqpqp_solve_tr(self.h, phase, _d(x_k), _d(delta), _d(E_override), _i(act), _d(p), _d(lam), _d(mxL),
+                                           _d(mxU), _d(slack), _i(status), info.ctypes.data_as(C.c_void_p)))
         return p, lam, mxL, mxU, slack[:, :S], status, info
+
+    def solve_tr_mixed(self, x_k, delta, active_qp, active_fr):
+        """One SQP round of a batch with instances in both phases (sqpqp_solve_tr_mixed): QP subproblems over `active_qp`,
+        restoration LPs over `active_fr` (disjoint), launched side by side; one set of results."""
+        return self.solve_tr(None, x_k, delta, mixed=(active_qp, active_fr))
+
+    def solve_tr_mixed_device(self, x_k_ptr, delta_ptr, active_qp_ptr, active_fr_ptr):
+        self._ck(self.L.sqpqp_solve_tr_mixed_device(self.h, x_k_ptr, delta_ptr, active_qp_ptr, active_fr_ptr))
 
     def solve_tr_device(self, phase, x_k_ptr, delta_ptr, E_override_ptr=None, active_ptr=None):
         """Device-pointer, non-blocking variant (ints are raw device addresses)."""

@@ -36,6 +36,8 @@ struct sqpqp_handle_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // pair in use (one of tev[], or the SpMV pair)
     cudaEvent_t tev[4][2] = {};                 // ring of event pairs of the solve launches
     cudaEvent_t sev[2] = {};                    // pair of the SpMV timing
+    cudaStream_t stream2 = nullptr;             // side stream (highest priority) of the mixed-phase launch: the restoration-phase kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // runs next to the QP-phase kernel of the same round (launch_solve_mixed)
     int tp_head = 0, tp_n = 0;
     std::string err;
     sqpqp_options opts;
@@ -381,6 +383,16 @@ extern "C" int sqpqp_create(sqpqp_handle* out, int device) {
         delete h;
         return SQPQP_E_CUDA;
     }
+    {   // side stream of the mixed-phase launch, at the highest priority: its few CTAs start as soon as any slot frees
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            delete h;
+            return SQPQP_E_CUDA;
+        }
+    }
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -426,6 +438,9 @@ extern "C" int sqpqp_destroy(sqpqp_handle h) {
     for (auto& pr : h->tev) for (auto e : pr) if (e) cudaEventDestroy(e);
     for (auto e : h->sev) if (e) cudaEventDestroy(e);
     for (auto e : h->evpool) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -1264,17 +1279,19 @@ __global__ void __launch_bounds__(256) k_rank_unfinished(const IpmState* __restr
     if (i < B) order[rank] = i;
 }
 
-static int launch_solve(sqpqp_handle h, int phase) {
-    Prob& P = h->P;
-    const size_t B = P.batch;
-    DevOpts O{h->opts, 0, 0};
+static int solve_team(sqpqp_handle h, int phase) {
+    const Prob& P = h->P;
     int team = h->opts.team;
-    if (team == 0) team = (B == 1 && (size_t)P.Ne + P.m > 6000) ? 2 : 1;
+    if (team == 0) team = (P.batch == 1 && (size_t)P.Ne + P.m > 6000) ? 2 : 1;
     // a dense tail laid out for the CTA team (panels of 4, shared memory) cannot be run by the grid team and vice versa
     if (team == 2 && ((phase == SQPQP_PHASE_FR ? P.chol_fr.T : P.chol.T) > 0) && !(phase == SQPQP_PHASE_FR ? P.Dtail_fr : P.Dtail)) team = 1;
     if (team == 1 && ((phase == SQPQP_PHASE_FR ? P.chol_fr.T : P.chol.T) > 0) && (phase == SQPQP_PHASE_FR ? P.Dtail_fr : P.Dtail)) team = 2;
-    // event pair of this launch: a small ring, so that back-to-back launches (QP phase, then restoration phase) need no host
-    // synchronisation between them; a slot is only waited for when the ring wraps around to it
+    return team;
+}
+
+// event pair of a solve launch: a small ring, so that back-to-back launches need no host synchronisation between them; a slot
+// is only waited for when the ring wraps around to it
+static int begin_solve_timing(sqpqp_handle h) {
     if (h->timing_pending && h->timing_is_solve && h->tp_n == kTimingRing) sqpqp_last_solve_ms(h);
     if (!h->timing_is_solve && h->timing_pending) sqpqp_last_solve_ms(h);
     {
@@ -1282,9 +1299,25 @@ static int launch_solve(sqpqp_handle h, int phase) {
         h->ev0 = h->tev[slot][0]; h->ev1 = h->tev[slot][1];
     }
     CUDA_OK(cudaEventRecord(h->ev0, h->stream));
+    return 0;
+}
+static int end_solve_timing(sqpqp_handle h) {
+    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
+    h->timing_pending = true;
+    h->timing_is_solve = true;
+    h->tp_n++;
+    return 0;
+}
+
+// the kernels of ONE phase (interior-point launch, hand-off launch, masked ADMM launch) on stream st
+static int launch_solve_kernels(sqpqp_handle h, int phase, cudaStream_t st) {
+    Prob& P = h->P;
+    const size_t B = P.batch;
+    DevOpts O{h->opts, 0, 0};
+    const int team = solve_team(h, phase);
     if (team == 2) {
         void* args[] = {(void*)&P, (void*)&O, (void*)&phase};
-        CUDA_OK(cudaLaunchCooperativeKernel((void*)k_solve_grid, dim3(h->coop_blocks), dim3(256), args, 0, h->stream));
+        CUDA_OK(cudaLaunchCooperativeKernel((void*)k_solve_grid, dim3(h->coop_blocks), dim3(256), args, 0, st));
         h->last_kernel = "k_solve_grid";
     } else {
         int threads = pick_threads(h, phase);
@@ -1330,17 +1363,17 @@ static int launch_solve(sqpqp_handle h, int phase) {
         const int cfg = (occ >= 3 && threads <= 256) ? 4 : (occ >= 2 ? 2 : 1);
         auto launch = [&](int mode, const DevOpts& OO) {
             if (cfg == 4) {
-                if (mode == 1) k_solve_cta<256, 4, 1><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
-                else k_solve_cta<256, 4, 2><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
+                if (mode == 1) k_solve_cta<256, 4, 1><<<grid, threads, dyn, st>>>(P, OO, phase, pl);
+                else k_solve_cta<256, 4, 2><<<grid, threads, dyn, st>>>(P, OO, phase, pl);
             } else if (cfg == 2 && threads <= 384) {  // 85 registers per thread instead of 64
-                if (mode == 1) k_solve_cta<384, 2, 1><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
-                else k_solve_cta<384, 2, 2><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
+                if (mode == 1) k_solve_cta<384, 2, 1><<<grid, threads, dyn, st>>>(P, OO, phase, pl);
+                else k_solve_cta<384, 2, 2><<<grid, threads, dyn, st>>>(P, OO, phase, pl);
             } else if (cfg == 2) {
-                if (mode == 1) k_solve_cta<512, 2, 1><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
-                else k_solve_cta<512, 2, 2><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
+                if (mode == 1) k_solve_cta<512, 2, 1><<<grid, threads, dyn, st>>>(P, OO, phase, pl);
+                else k_solve_cta<512, 2, 2><<<grid, threads, dyn, st>>>(P, OO, phase, pl);
             } else {
-                if (mode == 1) k_solve_cta<512, 1, 1><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
-                else k_solve_cta<512, 1, 2><<<grid, threads, dyn, h->stream>>>(P, OO, phase, pl);
+                if (mode == 1) k_solve_cta<512, 1, 1><<<grid, threads, dyn, st>>>(P, OO, phase, pl);
+                else k_solve_cta<512, 1, 2><<<grid, threads, dyn, st>>>(P, OO, phase, pl);
             }
             h->launches++;
         };
@@ -1381,14 +1414,14 @@ static int launch_solve(sqpqp_handle h, int phase) {
                 O2.handoff_k = 0; O2.resume = 1;
                 int t2 = pick_threads(h, phase);
                 if (t2 > 512) t2 = 512;
-                k_solve_cta<512, 1, 1><<<grid, t2, dyn2, h->stream>>>(P, O2, phase, pl2);
+                k_solve_cta<512, 1, 1><<<grid, t2, dyn2, st>>>(P, O2, phase, pl2);
                 h->launches++;
             } else if (quota > 0 && (hmode == 1 || hmode == 3)) {
                 // second stage in the same launch configuration: every instance the quota stopped, longest predicted first
                 DevOpts O2 = O;
                 O2.handoff_k = 0; O2.resume = 1; O2.order = nullptr;
                 if (hmode == 1 && B <= 16384) {
-                    k_rank_unfinished<<<(unsigned)((B + 255) / 256), 256, 0, h->stream>>>(P.ipm_state, P.fb_flag, h->d_order, (int)B, h->opts.ipm_rho0);
+                    k_rank_unfinished<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(P.ipm_state, P.fb_flag, h->d_order, (int)B, h->opts.ipm_rho0);
                     h->launches++;
                     O2.order = h->d_order;
                 }
@@ -1398,18 +1431,59 @@ static int launch_solve(sqpqp_handle h, int phase) {
             if (quota > 0) h->last_kernel += hmode == 0 ? "+handoff" : (hmode == 1 ? "+resume(ranked)" : (hmode == 3 ? "+resume" : "+stop"));
         } else {  // no factorisation available: every instance is "flagged" (non-zero) for the ADMM launch
             h->last_kernel = "k_solve_cta<..,2> (ADMM)";
-            CUDA_OK(cudaMemsetAsync(P.fb_flag, 1, B * sizeof(int), h->stream));
+            CUDA_OK(cudaMemsetAsync(P.fb_flag, 1, B * sizeof(int), st));
         }
         if (h->opts.method != 2) launch(2, O);
         h->launches--;  // counted below
     }
     h->launches++;
-    CUDA_OK(cudaEventRecord(h->ev1, h->stream));
-    h->timing_pending = true;
-    h->timing_is_solve = true;
-    h->tp_n++;
     return 0;
 }
+
+static int launch_solve(sqpqp_handle h, int phase) {
+    int rc = begin_solve_timing(h);
+    if (rc) return rc;
+    rc = launch_solve_kernels(h, phase, h->stream);
+    if (rc) return rc;
+    return end_solve_timing(h);
+}
+
+// One SQP round of a batch whose instances are in different phases (compute_step!, sqp_trust_region.jl:370-380, per instance):
+// the QP-phase launch over `act_qp` and the restoration-phase launch over `act_fr` touch disjoint instances, so they run
+// CONCURRENTLY -- the restoration kernel on the high-priority side stream, forked behind everything queued on the main stream and
+// joined back into it.  Measured on the 1024-instance batch (tools/gpu_phase_share.py): a round has at most a few instances in
+// restoration, and their launch, run after the QP launch, kept ONE CTA busy for 9-20 ms while the GPU idled -- 58 restoration
+// solves of 102 k subproblems were 8.8 % of the solve time of the whole run.
+static int launch_solve_mixed(sqpqp_handle h, const int* act_qp, const int* act_fr) {
+    Prob& P = h->P;
+    const bool concurrent = P.has_chol && P.has_chol_fr && h->opts.method != 1 && h->handoff_mode == 0 && !(h->G > 1) &&
+                            solve_team(h, SQPQP_PHASE_QP) == 1 && solve_team(h, SQPQP_PHASE_FR) == 1;
+    int rc = begin_solve_timing(h);
+    if (rc) return rc;
+    if (concurrent) {
+        CUDA_OK(cudaEventRecord(h->ev_fork, h->stream));
+        CUDA_OK(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+        P.active = act_fr;
+        rc = launch_solve_kernels(h, SQPQP_PHASE_FR, h->stream2);
+        if (rc) return rc;
+        CUDA_OK(cudaEventRecord(h->ev_join, h->stream2));
+        P.active = act_qp;
+        rc = launch_solve_kernels(h, SQPQP_PHASE_QP, h->stream);
+        if (rc) return rc;
+        CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        h->last_kernel += " || restoration phase on the side stream";
+    } else {
+        P.active = act_qp;
+        rc = launch_solve_kernels(h, SQPQP_PHASE_QP, h->stream);
+        if (rc) return rc;
+        P.active = act_fr;
+        rc = launch_solve_kernels(h, SQPQP_PHASE_FR, h->stream);
+        if (rc) return rc;
+    }
+    P.active = nullptr;
+    return end_solve_timing(h);
+}
+
 
 extern "C" int sqpqp_solve_tr(sqpqp_handle h, int32_t phase, const double* x_k, const double* delta, const double* E_override,
                               const int32_t* active, double* p, double* lambda, double* mult_x_L, double* mult_x_U,
@@ -1469,6 +1543,65 @@ extern "C" int sqpqp_solve_tr_device(sqpqp_handle h, int32_t phase, const double
     P.active = nullptr;
     P.Eov = nullptr;
     return rc;
+}
+
+// Both phases of one SQP round in one call: instances with active_qp[b] != 0 solve the QP subproblem (sub_optimize!), instances
+// with active_fr[b] != 0 the restoration LP (sub_optimize_FR!); the two sets must be disjoint, every other instance is skipped.
+// One upload of x_k / delta, the two launches side by side (launch_solve_mixed), one download of the results.
+extern "C" int sqpqp_solve_tr_mixed(sqpqp_handle h, const double* x_k, const double* delta, const int32_t* active_qp,
+                                    const int32_t* active_fr, double* p, double* lambda, double* mult_x_L, double* mult_x_U,
+                                    double* slack, int32_t* moi_status, sqpqp_info* info) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
+    if (!x_k || !delta || !active_qp || !active_fr) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    const size_t B = P.batch;
+    for (size_t b = 0; b < B; ++b) {
+        if (active_qp[b] && active_fr[b]) return fail(h, SQPQP_E_BADARG, "an instance is in one phase per round: active_qp and active_fr overlap");
+        if (!(delta[b] > 0.0)) return fail(h, SQPQP_E_BADARG, "delta must be positive");
+    }
+    size_t bytes = B * ((size_t)3 * P.n + 2 * (size_t)P.m + P.S + 8) * sizeof(double) * 2 + B * (sizeof(sqpqp_info) + 32) + 16384;
+    int rc = ensure_stage(h, bytes);
+    if (rc) return rc;
+    P.xk = upload(h, x_k, B * P.n);
+    P.delta = upload(h, delta, B);
+    P.Eov = nullptr;
+    const int* aq = upload(h, active_qp, B);
+    const int* af = upload(h, active_fr, B);
+    rc = launch_solve_mixed(h, aq, af);
+    if (rc) return rc;
+    download(h, P.o_p, p, B * P.n);
+    download(h, P.o_lam, lambda, B * P.m);
+    download(h, P.o_mxL, mult_x_L, B * P.n);
+    download(h, P.o_mxU, mult_x_U, B * P.n);
+    download(h, P.o_slack, slack, B * P.S);
+    download(h, P.o_info, info, B);
+    std::vector<sqpqp_info> tmp;
+    if (moi_status && !info) {
+        tmp.resize(B);
+        download(h, P.o_info, tmp.data(), B);
+    }
+    rc = finish(h);
+    if (rc) return rc;
+    if (moi_status) {
+        const sqpqp_info* src = info ? info : tmp.data();
+        for (size_t b = 0; b < B; ++b) moi_status[b] = (active_qp[b] || active_fr[b]) ? src[b].moi_status : moi_status[b];
+    }
+    return 0;
+}
+
+// Device-pointer variant of sqpqp_solve_tr_mixed (nothing crosses PCIe, nothing blocks; the masks are device arrays and the
+// caller guarantees that they are disjoint).
+extern "C" int sqpqp_solve_tr_mixed_device(sqpqp_handle h, const double* x_k, const double* delta, const int32_t* active_qp,
+                                           const int32_t* active_fr) {
+    if (!h) return SQPQP_E_BADARG;
+    if (!h->setup_done || !h->updated) return fail(h, SQPQP_E_STATE, "setup/update not called");
+    if (!x_k || !delta || !active_qp || !active_fr) return fail(h, SQPQP_E_BADARG, "null pointer");
+    DeviceGuard g(h->device);
+    Prob& P = h->P;
+    P.xk = x_k; P.delta = delta; P.Eov = nullptr;
+    return launch_solve_mixed(h, active_qp, active_fr);
 }
 
 extern "C" int sqpqp_sync(sqpqp_handle h) {

@@ -89,6 +89,7 @@ class BatchSqpTR:
         self.device_evaluator = bool(device_evaluator)
         if self.device_evaluator:
             self.optimizer.engine.acopf_setup(nlp)
+        self.mixed_phases = True  # a round with instances in both phases is ONE engine call (False: one call per phase)
         self.rounds = 0
         self.timers = {"callbacks": 0.0, "device": 0.0}
         self.trace = None
@@ -191,7 +192,12 @@ class BatchSqpTR:
             qp_mask = act & ~self.feasibility_restoration
             fr_mask = act & self.feasibility_restoration
             new_lam = np.zeros_like(self.lam); new_U = np.zeros_like(self.mult_x_U); new_L = np.zeros_like(self.mult_x_L)
-            for mask, fn in ((qp_mask, self.optimizer.sub_optimize), (fr_mask, self.optimizer.sub_optimize_FR)):
+            # instances in both phases: one call, the two launches side by side (sqpqp_solve_tr_mixed); else the phase's own call
+            if self.mixed_phases and qp_mask.any() and fr_mask.any():
+                calls = ((act, lambda x, d, active: self.optimizer.sub_optimize_mixed(x, d, qp_mask.astype(np.int32), fr_mask.astype(np.int32))),)
+            else:
+                calls = ((qp_mask, self.optimizer.sub_optimize), (fr_mask, self.optimizer.sub_optimize_FR))
+            for mask, fn in calls:
                 if mask.any():
                     p, lam, mxU, mxL, _, st = fn(self.x, self.Delta, active=mask.astype(np.int32))
                     self.p[mask] = p[mask]; new_lam[mask] = lam[mask]; new_U[mask] = mxU[mask]; new_L[mask] = mxL[mask]

@@ -52,7 +52,11 @@ class QpDevice:
         self.engine.update_nlp(dE, h_val, df, E)
 
     def _solve(self, phase, x_k, delta, E_override=None, active=None):
-        p, lam, mxL, mxU, slack, status, info = self.engine.solve_tr(phase, x_k, delta, E_override, active)
+        if phase == capi.PHASE_MIXED:  # active = (mask of the QP phase, mask of the restoration phase)
+            p, lam, mxL, mxU, slack, status, info = self.engine.solve_tr_mixed(x_k, delta, active[0], active[1])
+            active = np.asarray(active[0], bool) | np.asarray(active[1], bool)
+        else:
+            p, lam, mxL, mxU, slack, status, info = self.engine.solve_tr(phase, x_k, delta, E_override, active)
         sel = slice(None) if active is None else np.asarray(active, bool)
         st = self.stats
         st["solves"] += 1
@@ -69,6 +73,11 @@ class QpDevice:
 
     def sub_optimize_FR(self, x_k, delta, active=None):
         return self._solve(capi.PHASE_FR, x_k, delta, None, active)
+
+    def sub_optimize_mixed(self, x_k, delta, active_qp, active_fr):
+        """One round of compute_step! (sqp_trust_region.jl:370-380) over a batch with instances in BOTH phases: sub_optimize!
+        for `active_qp`, sub_optimize_FR! for `active_fr` (disjoint masks), one call -- the two launches run side by side."""
+        return self._solve(capi.PHASE_MIXED, x_k, delta, None, (active_qp, active_fr))
 
     def sub_optimize_soc(self, x_k, delta, E_soc, active=None):
         return self._solve(capi.PHASE_SOC, x_k, delta, E_soc, active)

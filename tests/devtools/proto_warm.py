@@ -136,9 +136,11 @@ if __name__ == "__main__":
     from sqpsolver_jl_b200.nlp.acopf import AcopfPolar
     from sqpsolver_jl_b200.nlp.networks import synth_net
     pairs = pickle.load(open(sys.argv[1], "rb"))
-    nlp = AcopfPolar(synth_net(118, 186, 54, 118))
+    net = synth_net(118, 186, 54, 118)
+    nlp0 = AcopfPolar(net)
 
     def qp(t):
+        nlp = AcopfPolar(net, pd=t["pd"], qd=t["qd"]) if "pd" in t else nlp0  # pairs of the perturbed-load batch carry their loads
         J = CooMatrix(nlp.j_row, nlp.j_col, nlp.m, nlp.n); J.fill(t["dE"])
         H = SymCooMatrix(nlp.h_row, nlp.h_col, nlp.n); H.fill(t["h_val"])
         lb, ub = trust_region_box(nlp.x_L - t["x"], nlp.x_U - t["x"], t["Delta"])

@@ -651,3 +651,45 @@ def test_error_paths(engine):
     _setup(engine, nlp)
     with pytest.raises(capi.SqpQpError):
         engine.solve_tr(capi.PHASE_QP, np.zeros(1), 1.0)  # solve before update
+
+
+@pytest.mark.parametrize("B", [6, 200])
+def test_mixed_phase_round_equals_the_two_sequential_calls(engine, B):
+    """sqpqp_solve_tr_mixed: one SQP round of a batch with instances in both phases (compute_step!, sqp_trust_region.jl:370-380)
+    -- the QP-phase launch and the restoration-phase launch run side by side on two streams over disjoint instances.  The
+    results must be the bits the two sequential sqpqp_solve_tr calls give (same kernels, same data), untouched instances stay
+    untouched, and overlapping masks are refused.  B = 200: more instances than SMs (two CTAs per SM, throughput launch)."""
+    g = np.load(os.path.join(GOLD, "case9_mu1e4.npz"))
+    nlp = AcopfPolar(case9())
+    _setup(engine, nlp, batch=B)
+    engine.set_options(warm_start=0)
+    rng = np.random.default_rng(11)
+    ks = rng.integers(1, g["qp_x"].shape[0], size=B)  # a different recorded subproblem per instance
+    dE, hv, df, E, x = (np.stack([g[k][i] for i in ks]) for k in ("qp_dE", "qp_h_val", "qp_df", "qp_E", "qp_x"))
+    delta = np.array([float(g["qp_Delta"][i]) for i in ks])
+    engine.update_nlp(dE, hv, df, E)
+    which = rng.integers(0, 3, size=B)  # 0: QP phase, 1: restoration phase, 2: not in this round
+    aq, af = (which == 0).astype(np.int32), (which == 1).astype(np.int32)
+    assert aq.any() and af.any() and (which == 2).any()
+    seq_q = [v.copy() for v in engine.solve_tr(capi.PHASE_QP, x, delta, active=aq)]
+    seq_f = [v.copy() for v in engine.solve_tr(capi.PHASE_FR, x, delta, active=af)]
+    # results of the sequential pair: an instance's outputs come from the call of its phase
+    want = [np.where((aq.astype(bool))[(...,) + (None,) * (a.ndim - 1)], a, b) for a, b in zip(seq_q[:6], seq_f[:6])]
+    # poison the device-side outputs of the skipped instances with a different solve, then run the mixed round
+    engine.solve_tr(capi.PHASE_QP, x, delta * 0.5, active=(which == 2).astype(np.int32))
+    skipped_before = [v.copy() for v in engine.solve_tr(capi.PHASE_QP, x, delta * 0.5, active=(which == 2).astype(np.int32))[:4]]
+    mix = engine.solve_tr_mixed(x, delta, aq, af)
+    assert "side stream" in engine.last_solve_kernel
+    act = (which != 2)
+    for a, b in zip(want[:5], mix[:5]):
+        assert np.array_equal(a[act], b[act])
+    assert np.array_equal(np.asarray(want[5])[act], np.asarray(mix[5])[act])  # statuses
+    assert np.isin(np.asarray(mix[5])[aq.astype(bool)], (capi.MOI_LOCALLY_SOLVED, capi.MOI_ALMOST_LOCALLY_SOLVED, capi.MOI_LOCALLY_INFEASIBLE)).all()
+    for a, b in zip(skipped_before, mix[:4]):  # instances outside both masks keep what the device held for them
+        assert np.array_equal(a[~act], b[~act])
+    info_q, info_f, info_m = seq_q[6], seq_f[6], mix[6]
+    assert np.array_equal(info_m["ipm_iters"][aq.astype(bool)], info_q["ipm_iters"][aq.astype(bool)])
+    assert np.array_equal(info_m["ipm_iters"][af.astype(bool)], info_f["ipm_iters"][af.astype(bool)])
+    bad = af.copy(); bad[np.nonzero(aq)[0][0]] = 1
+    with pytest.raises(capi.SqpQpError):
+        engine.solve_tr_mixed(x, delta, aq, bad)
