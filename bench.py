@@ -209,7 +209,15 @@ class ClockSampler:
         self.proc = None
         self.gpu = gpu_index
 
-    def start(self):
+    def start(self, wait_s=3.0):
+        """Starts the sampler and waits for its first row: the start-up of nvidia-smi (NVML initialisation) must not fall into the
+        timed region -- it can hold up the thread that enqueues the launches, and the GPU runs dry."""
+        self._start()
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < wait_s:
+            time.sleep(0.02)
+
+    def _start(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -335,7 +343,13 @@ def main():
     ap.add_argument("--layout-threads", dest="layout_threads", type=int, default=0)
     ap.add_argument("--layout-ctas", dest="layout_ctas", type=int, default=0)
     ap.add_argument("--layout-tail", dest="layout_tail", type=int, default=-1)
+    ap.add_argument("--layout-handoff", dest="layout_handoff", type=int, default=None,
+                    help="iteration quota before the resident launch takes an instance over (-1 auto, 0 off)")
     ap.add_argument("--no-single2000", action="store_true", help="skip the single-instance 2000-bus leg (BASELINE configs[3])")
+    ap.add_argument("--groups", type=int, default=0,
+                    help="independent groups of instances per GPU, each with its own engine handle / stream / host thread "
+                         "(0 = auto: 4 from 768 instances per GPU, else 2; 1 = lock-step batch)")
+    ap.add_argument("--repeats", type=int, default=3, help="the K-step timed region is run this many times; the MEDIAN is reported")
     ap.add_argument("--sequential-phases", dest="sequential_phases", action="store_true",
                     help="A/B: QP-phase and restoration-phase launches of a round one after the other (two calls) instead of side by side")
     args = ap.parse_args()
@@ -347,7 +361,7 @@ def main():
 
     from sqpsolver_jl_b200 import capi
     from sqpsolver_jl_b200.host.batch import gather_results, pack_results, shard_range
-    from sqpsolver_jl_b200.host.sqp_trust_region import BatchSqpTR, Parameters
+    from sqpsolver_jl_b200.host.sqp_trust_region import GroupedBatchSqpTR, Parameters
     from sqpsolver_jl_b200.nlp.acopf import AcopfPolar
 
     rank = int(os.environ.get("RANK", "0"))
@@ -373,150 +387,220 @@ def main():
     nlp = AcopfPolar(net, pd=pd, qd=qd)
     kw = sqp_params(args)
 
-    # ---- untimed set-up: run the real batched SQP on the device, record the first rounds ----
-    rec = []
-
+    # ---- untimed set-up: run the real batched SQP on the device, record rounds sampled over the whole solve ----
+    # The shard is driven as G independent groups of instances (GroupedBatchSqpTR: one engine handle, stream and host thread per
+    # group): the launches of the other group fill the straggler tail of a launch and the host work between rounds.
+    # measured (profiles/r02_tuning.md section 10): 1024 instances per GPU 71.3 / 60.2 / 57.5 ms per step with 1 / 2 / 4 groups
+    # (cont.) finer groups keep helping until a group has about 32 instances: 256 per GPU 28.7 / 22.3 / 22.0 / 19.2 ms with
+    # 1 / 2 / 4 / 8 groups, 128 per GPU 18.7 / 18.4 / 17.5 / 17.8 / 26.9 with 1 / 2 / 4 / 8 / 16, 512 per GPU 35.9 / 33.7 with 2 / 4
+    G = args.groups if args.groups > 0 else (4 if Bl >= 512 else max(2, min(8, Bl // 32)))
+    G = max(1, min(G, Bl))
     layout = dict(G=args.layout_G, threads=args.layout_threads, ctas_per_sm=args.layout_ctas, tail=args.layout_tail)
-    sqp = BatchSqpTR(nlp, Bl, Parameters(**kw), device=local, layout=layout)
-    sqp.mixed_phases = not args.sequential_phases
+    if args.layout_handoff is not None:
+        layout["handoff"] = args.layout_handoff
+    sqp = GroupedBatchSqpTR(nlp, Bl, Parameters(**kw), groups=G, device=local, layout=layout)
+    G = len(sqp.subs)
+    gb = sqp.bounds
     # replayed rounds are sampled UNIFORMLY over the whole solve (round 1, 1 + T/R, ...): late rounds carry the stragglers
     stride = max(1, args.sqp_max_iter // max(1, args.rounds))
     sample_rounds = {1 + k * stride for k in range(args.rounds)}
-    # record at the moment of each QP call: hook the stats counter via the merit call order
-    orig_solve = sqp.optimizer._solve
+    rec = [[] for _ in range(G)]  # per group: the recorded rounds (inputs of the hot path at the moment of the solve call)
 
-    def solve_hook(phase, x_k, delta, E_override=None, active=None):
-        if phase == capi.PHASE_MIXED and sqp.rounds in sample_rounds:  # both phases of the round in one call
-            rec.append({"round": sqp.rounds, "dE": sqp.dE.copy(), "h_val": sqp.h_val.copy(), "df": sqp.df.copy(),
-                        "E": sqp.E.copy(), "x": sqp.x.copy(), "Delta": sqp.Delta.copy(),
-                        "qp": np.asarray(active[0], np.int32).copy(), "fr": np.asarray(active[1], np.int32).copy(),
-                        "lam": sqp.lam.copy(), "mxU": sqp.mult_x_U.copy(), "mxL": sqp.mult_x_L.copy(),
-                        "mu": sqp.mu.copy(), "f": sqp.f.copy()})
-        elif phase in (capi.PHASE_QP, capi.PHASE_FR) and sqp.rounds in sample_rounds:
-            act = np.ones(Bl, bool) if active is None else np.asarray(active, bool)
-            if rec and rec[-1].get("round") == sqp.rounds:
-                rec[-1]["fr" if phase == capi.PHASE_FR else "qp"] = act.astype(np.int32)
-            else:
-                z = np.zeros(Bl, np.int32)
-                rec.append({"round": sqp.rounds, "dE": sqp.dE.copy(), "h_val": sqp.h_val.copy(), "df": sqp.df.copy(),
-                            "E": sqp.E.copy(), "x": sqp.x.copy(), "Delta": sqp.Delta.copy(),
-                            "qp": act.astype(np.int32) if phase == capi.PHASE_QP else z,
-                            "fr": act.astype(np.int32) if phase == capi.PHASE_FR else z,
-                            "lam": sqp.lam.copy(), "mxU": sqp.mult_x_U.copy(), "mxL": sqp.mult_x_L.copy(),
-                            "mu": sqp.mu.copy(), "f": sqp.f.copy()})
-        return orig_solve(phase, x_k, delta, E_override, active)
+    def make_hook(g, sub):
+        orig_solve = sub.optimizer._solve
+        Bg = gb[g][1] - gb[g][0]
 
-    sqp.optimizer._solve = solve_hook
+        def snap(qp, fr):
+            return {"round": sub.rounds, "dE": sub.dE.copy(), "h_val": sub.h_val.copy(), "df": sub.df.copy(), "E": sub.E.copy(),
+                    "x": sub.x.copy(), "Delta": sub.Delta.copy(), "qp": qp, "fr": fr, "lam": sub.lam.copy(),
+                    "mxU": sub.mult_x_U.copy(), "mxL": sub.mult_x_L.copy(), "mu": sub.mu.copy(), "f": sub.f.copy()}
+
+        def solve_hook(phase, x_k, delta, E_override=None, active=None):
+            if sub.rounds in sample_rounds:
+                if phase == capi.PHASE_MIXED:  # both phases of the round in one call
+                    rec[g].append(snap(np.asarray(active[0], np.int32).copy(), np.asarray(active[1], np.int32).copy()))
+                elif phase in (capi.PHASE_QP, capi.PHASE_FR):
+                    act = (np.ones(Bg, bool) if active is None else np.asarray(active, bool)).astype(np.int32)
+                    if rec[g] and rec[g][-1]["round"] == sub.rounds:
+                        rec[g][-1]["fr" if phase == capi.PHASE_FR else "qp"] = act
+                    else:
+                        z = np.zeros(Bg, np.int32)
+                        rec[g].append(snap(act if phase == capi.PHASE_QP else z, act if phase == capi.PHASE_FR else z))
+            return orig_solve(phase, x_k, delta, E_override, active)
+
+        sub.optimizer._solve = solve_hook
+
+    for g, sub in enumerate(sqp.subs):
+        sub.mixed_phases = not args.sequential_phases
+        make_hook(g, sub)
     t0 = time.perf_counter()
     sqp.run()
     t_sqp = time.perf_counter() - t0
-    full = {"wall_s": t_sqp, "rounds": int(sqp.rounds), "sqp_iterations": int(sqp.iter.sum() - Bl + (sqp.ret != -1).sum()),
+    full = {"wall_s": t_sqp, "groups": G, "rounds": int(sqp.rounds), "sqp_iterations": int(sqp.iter.sum() - Bl + (sqp.ret != -1).sum()),
             "qp_solves": int(sqp.n_qp.sum()), "status_counts": {int(k): int(v) for k, v in zip(*np.unique(sqp.status, return_counts=True))},
             "device_s": sqp.timers["device"], "callbacks_s": sqp.timers["callbacks"],
-            "solve_kernel_s": sqp.optimizer.stats["solve_ms"] / 1e3}
+            "solve_kernel_s": sqp.stats["solve_ms"] / 1e3}
     full["qp_solves_per_sec_wall"] = full["qp_solves"] / t_sqp                      # host NLP callbacks + PCIe + kernels
     full["qp_solves_per_sec_kernel"] = full["qp_solves"] / max(full["solve_kernel_s"], 1e-9)
     full["ms_per_round_kernel"] = 1e3 * full["solve_kernel_s"] / max(1, full["rounds"])
     full["converged_instances"] = int((sqp.status == 0).sum())
+    full["note"] = ("device_s / callbacks_s / solve_kernel_s are summed over the %d groups, whose launches and host work overlap: they do "
+                    "not add up to wall_s" % G) if G > 1 else ""
     res_local = pack_results(sqp.status, sqp.iter, sqp.obj_val)
     res_all = gather_results(res_local, batch, device=dev)  # the one collective of the path (NCCL, 16 B/instance)
-    eng = sqp.optimizer.engine
-    R = len(rec)
+    engs = [sub.optimizer.engine for sub in sqp.subs]
+    eng = engs[0]
+    R = min(len(r) for r in rec)
     assert R > 0
-    S_launch0 = eng.launch_count
 
     # device-resident copies of the recorded inputs (for `value`)
-    drec = []
-    for r in rec:
-        d = {k: torch.from_numpy(np.ascontiguousarray(r[k])).to(dev) for k in ("dE", "h_val", "df", "E", "x", "Delta", "qp", "fr")}
-        drec.append(d)
+    drec = [[{k: torch.from_numpy(np.ascontiguousarray(r[k])).to(dev) for k in ("dE", "h_val", "df", "E", "x", "Delta", "qp", "fr")}
+             for r in rec[g][:R]] for g in range(G)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+    streams = [torch.cuda.ExternalStream(e.stream, device=dev) for e in engs]
     ptr = lambda t: t.data_ptr()
 
-    def step_device(j):
-        d = drec[j % R]
+    def step_device(g, j):
+        e, d, r = engs[g], drec[g][j % R], rec[g][j % R]
         if j % R == 0:
-            eng.set_options(warm_start=0)  # round 1 of a solve is cold
-        eng.update_nlp_device(ptr(d["dE"]), ptr(d["h_val"]), ptr(d["df"]), ptr(d["E"]))
-        nq, nf = int(rec[j % R]["qp"].sum()), int(rec[j % R]["fr"].sum())
+            e.set_options(warm_start=0)  # round 1 of a solve is cold
+        e.update_nlp_device(ptr(d["dE"]), ptr(d["h_val"]), ptr(d["df"]), ptr(d["E"]))
+        nq, nf = int(r["qp"].sum()), int(r["fr"].sum())
         if nq and nf and not args.sequential_phases:  # instances in both phases: one call, the two launches side by side
-            eng.solve_tr_mixed_device(ptr(d["x"]), ptr(d["Delta"]), ptr(d["qp"]), ptr(d["fr"]))
+            e.solve_tr_mixed_device(ptr(d["x"]), ptr(d["Delta"]), ptr(d["qp"]), ptr(d["fr"]))
         else:
             if nq:
-                eng.solve_tr_device(capi.PHASE_QP, ptr(d["x"]), ptr(d["Delta"]), None, ptr(d["qp"]))
+                e.solve_tr_device(capi.PHASE_QP, ptr(d["x"]), ptr(d["Delta"]), None, ptr(d["qp"]))
             if nf:
-                eng.solve_tr_device(capi.PHASE_FR, ptr(d["x"]), ptr(d["Delta"]), None, ptr(d["fr"]))
+                e.solve_tr_device(capi.PHASE_FR, ptr(d["x"]), ptr(d["Delta"]), None, ptr(d["fr"]))
         if j % R == 0:
-            eng.set_options(warm_start=1)
+            e.set_options(warm_start=1)
 
-    p_zero = np.zeros_like(rec[0]["x"])
+    p_zero = [np.zeros_like(rec[g][0]["x"]) for g in range(G)]
 
-    def step_host(j):
-        r = rec[j % R]
+    def step_host(g, j):
+        e, r = engs[g], rec[g][j % R]
         if j % R == 0:
-            eng.set_options(warm_start=0)
-        eng.update_nlp(r["dE"], r["h_val"], r["df"], r["E"])
-        eng.merit(r["x"], p_zero, r["E"], r["f"], r["mu"])
-        eng.kt_residuals(r["lam"], r["mxU"], r["mxL"])
+            e.set_options(warm_start=0)
+        e.update_nlp(r["dE"], r["h_val"], r["df"], r["E"])
+        e.merit(r["x"], p_zero[g], r["E"], r["f"], r["mu"])
+        e.kt_residuals(r["lam"], r["mxU"], r["mxL"])
         out = None
         nq, nf = int(r["qp"].sum()), int(r["fr"].sum())
         if nq and nf and not args.sequential_phases:
-            out = eng.solve_tr_mixed(r["x"], r["Delta"], r["qp"], r["fr"])
+            out = e.solve_tr_mixed(r["x"], r["Delta"], r["qp"], r["fr"])
         else:
             if nq:
-                out = eng.solve_tr(capi.PHASE_QP, r["x"], r["Delta"], active=r["qp"])
+                out = e.solve_tr(capi.PHASE_QP, r["x"], r["Delta"], active=r["qp"])
             if nf:
-                out = eng.solve_tr(capi.PHASE_FR, r["x"], r["Delta"], active=r["fr"])
+                out = e.solve_tr(capi.PHASE_FR, r["x"], r["Delta"], active=r["fr"])
         if j % R == 0:
-            eng.set_options(warm_start=1)
+            e.set_options(warm_start=1)
         return out
 
     def barrier():
         torch.cuda.synchronize()
+        for e in engs:
+            e.sync()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps, warmup, collect_info=False):
-        for j in range(warmup):
-            step_fn(j)
-        eng.sync()
-        times, infos, solve_ms = [], [], []
-        units = 0
+    def units_of(steps, warmup):
+        return sum(int(rec[g][(warmup + j) % R]["qp"].sum() + rec[g][(warmup + j) % R]["fr"].sum()) for j in range(steps) for g in range(G))
+
+    def region_ms(starts, ends):
+        # device time of the region: from the first start event to the last end event (event timestamps are device-global)
+        return max(s_.elapsed_time(e_) for s_ in starts for e_ in ends)
+
+    def timed_device(steps, warmup, run_warmup=True):
+        """K steps of every group enqueued back to back on the groups' streams (device-pointer API: nothing blocks), so that a
+        group's next launch starts as soon as ITS previous one has drained -- the pipelining the grouped driver produces."""
+        for j in range(warmup if run_warmup else 0):
+            for g in range(G):
+                step_device(g, j)
         barrier()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
+        for g in range(G):
+            starts[g].record(streams[g])
         for j in range(steps):
-            flush.fill_(j & 0xFF)  # L2 flush between timed steps (256 MiB > 126 MB L2)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ms0 = eng.solve_ms_total if collect_info else 0.0
-            e0.record(stream)
-            step_fn(warmup + j)
-            e1.record(stream)
-            e1.synchronize()
-            times.append(e0.elapsed_time(e1))
-            r = rec[(warmup + j) % R]
-            units += int(r["qp"].sum() + r["fr"].sum())
-            if collect_info:
-                solve_ms.append(eng.solve_ms_total - ms0)  # every solve launch of the step (QP phase + restoration phase)
-                infos.append((eng.fetch_info(), (r["qp"] | r["fr"]).astype(bool)))
+            with torch.cuda.stream(streams[0]):
+                flush.fill_(j & 0xFF)  # 256 MiB written between the steps of group 0 (the per-step working set exceeds L2 anyway)
+            for g in range(G):
+                step_device(g, warmup + j)
+        for g in range(G):
+            ends[g].record(streams[g])
+        for e_ in ends:
+            e_.synchronize()
+        t = region_ms(starts, ends)
         barrier()
-        return float(np.sum(times)), units, infos, solve_ms
+        return float(t), units_of(steps, warmup)
+
+    def timed_host(steps, warmup, run_warmup=True):
+        """The same steps through the blocking host-buffer C ABI, one host thread per group (as GroupedBatchSqpTR runs them)."""
+        import threading
+        for j in range(warmup if run_warmup else 0):
+            for g in range(G):
+                step_host(g, j)
+        barrier()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(G)]
+        for g in range(G):
+            starts[g].record(streams[g])
+        errs = []
+
+        def work(g):
+            try:
+                for j in range(steps):
+                    step_host(g, warmup + j)
+            except BaseException as ex:  # noqa: BLE001
+                errs.append(ex)
+
+        th = [threading.Thread(target=work, args=(g,)) for g in range(G)]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        if errs:
+            raise errs[0]
+        for g in range(G):
+            ends[g].record(streams[g])
+        for e_ in ends:
+            e_.synchronize()
+        t = region_ms(starts, ends)
+        barrier()
+        return float(t), units_of(steps, warmup)
 
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = eng.launch_count
-    t_ms, units, infos, solve_ms = timed(step_device, args.steps, args.warmup, collect_info=True)
-    launches = eng.launch_count - l0
+    l0 = sum(e.launch_count for e in engs)
+    dev_regions = [timed_device(args.steps, args.warmup, k == 0) for k in range(max(1, args.repeats))]
+    t_ms, units = float(np.median([t for t, _ in dev_regions])), dev_regions[0][1]
+    launches = (sum(e.launch_count for e in engs) - l0) // max(1, args.repeats)
     clocks = sampler.stop()
-    eng.reuse_outputs = True  # the host owns one set of result buffers and hands them to every call (no 60 MB allocation per step)
-    # ... and page-locks its persistent arrays once (sqpqp_host_register), as the reference's host would its sqp.dE / h_val / df / E /
-    # x / lambda vectors: the calls then copy straight between those arrays and the device (no staging memcpy)
-    eng.register_outputs = True
-    for r in rec:
-        eng.register_host(*[r[k] for k in ("dE", "h_val", "df", "E", "x", "Delta", "lam", "mxU", "mxL", "mu", "f", "qp", "fr")])
-    eng.register_host(p_zero)
-    e_ms, e_units, _, _ = timed(step_host, args.steps, args.warmup)
+    # untimed pass over the same steps, one at a time: per-instance iteration / factorisation counts (bit-reproducible) for the
+    # bytes model, and the CUDA-event time of every solve launch run ALONE
+    infos, solve_ms = [], []
+    for j in range(args.steps):
+        for g in range(G):
+            ms0 = engs[g].solve_ms_total
+            step_device(g, args.warmup + j)
+            engs[g].sync()
+            r = rec[g][(args.warmup + j) % R]
+            infos.append((engs[g].fetch_info(), (r["qp"] | r["fr"]).astype(bool)))
+            solve_ms.append(engs[g].solve_ms_total - ms0)
+    for g in range(G):
+        e = engs[g]
+        e.reuse_outputs = True  # the host owns one set of result buffers and hands them to every call (no 60 MB allocation per step)
+        # ... and page-locks its persistent arrays once (sqpqp_host_register), as the reference's host would its sqp.dE / h_val / df /
+        # E / x / lambda vectors: the calls then copy straight between those arrays and the device (no staging memcpy)
+        e.register_outputs = True
+        for r in rec[g][:R]:
+            e.register_host(*[r[k] for k in ("dE", "h_val", "df", "E", "x", "Delta", "lam", "mxU", "mxL", "mu", "f", "qp", "fr")])
+        e.register_host(p_zero[g])
+    host_regions = [timed_host(args.steps, args.warmup, k == 0) for k in range(max(1, args.repeats))]
+    e_ms, e_units = float(np.median([t for t, _ in host_regions])), host_regions[0][1]
 
     # max over ranks of the time, sum over ranks of the units
     def allred(v, op):
@@ -539,11 +623,13 @@ def main():
         nnzJ, nnzH = int(ciJ.shape[0]), int(ciH.shape[0])
         chol = eng.chol_stats()
         alg = [algorithmic_bytes(i, sel, n, m, nnzJ, nnzH, chol) for i, sel in infos]
-        ipm_it = float(np.mean([i["ipm_iters"][sel].mean() for i, sel in infos])) if infos else 0.0
-        ipm_max = int(max([i["ipm_iters"][sel].max() for i, sel in infos])) if infos else 0
+        ipm_it = float(np.sum([i["ipm_iters"][sel].sum() for i, sel in infos]) / max(1, np.sum([sel.sum() for i, sel in infos]))) if infos else 0.0
+        ipm_max = int(max([i["ipm_iters"][sel].max() for i, sel in infos if sel.any()])) if infos else 0
         fallbacks = int(sum([(i["admm_iters"][sel] > 0).sum() for i, sel in infos]))
-        # the solve kernel of the last phase launched in each step
-        ach = [a / (ms * 1e-3) / 1e9 for a, ms in zip(alg, solve_ms) if ms > 0]
+        # algorithmic bytes of EVERY solve launch of the timed region over the device time of the region (the launches of the
+        # groups overlap, so a per-launch duration is not defined inside it); solve_ms: the same launches run one at a time
+        ach = [float(np.sum(alg)) / (t_ms * 1e-3) / 1e9] if t_ms > 0 else []
+        ach_alone = float(np.sum(alg)) / (float(np.sum(solve_ms)) * 1e-3) / 1e9 if np.sum(solve_ms) > 0 else None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -558,13 +644,14 @@ def main():
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
-            if kernel_name.startswith(tr.get("kernel", "?")) and tr.get("batch_per_gpu") == Bl and tr.get("workload") == args.workload:
+            # (a launch covers one group of the shard)
+            if kernel_name.startswith(tr.get("kernel", "?")) and tr.get("batch_per_gpu") == Bl // G and tr.get("workload") == args.workload:
                 traffic = tr
         except (OSError, ValueError):
             pass
         b_it, b_f = bytes_model_ipm(n, m, nnzJ, nnzH, max(chol["nnzL"], 1))
-        h2d = int(sum(rec[0][k].nbytes for k in ("dE", "h_val", "df", "E", "x", "Delta", "qp")) + rec[0]["x"].nbytes * 2
-                  + rec[0]["E"].nbytes * 2 + rec[0]["lam"].nbytes + 2 * rec[0]["mxU"].nbytes)
+        h2d = int(sum(sum(rec[g][0][k].nbytes for k in ("dE", "h_val", "df", "E", "x", "Delta", "qp")) + rec[g][0]["x"].nbytes * 2
+                      + rec[g][0]["E"].nbytes * 2 + rec[g][0]["lam"].nbytes + 2 * rec[g][0]["mxU"].nbytes for g in range(G)))
         d2h = int(Bl * (3 * n + m + max(eng.S, 1)) * 8 + Bl * capi.INFO_DTYPE.itemsize + Bl * 8 * 6)
         line = {
             "metric": METRIC, "value": units_all / (t_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -572,10 +659,19 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wname, "network": {"nbus": net.nbus, "nbranch": net.nbranch, "ngen": net.ngen, "seed": net.meta.get("seed")},
                        "n": n, "m": m, "nnzJ": nnzJ, "nnzH_sym": nnzH, "batch_total": batch, "batch_per_gpu": Bl, "sqp": kw,
-                       "step": "one SQP iteration over the shard: COO value scatter + batched QP-subproblem solve kernel",
-                       "replayed_rounds": R, "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                       "step": "one SQP iteration over the shard: COO value scatter + batched QP-subproblem solve kernel(s)",
+                       "groups_per_gpu": G,
+                       "pipelining": ("the shard is driven as %d independent groups of instances, each with its own engine handle and stream "
+                                      "(host/sqp_trust_region.py: GroupedBatchSqpTR); the K timed steps of every group are enqueued back to "
+                                      "back, so a group's next launch starts when ITS previous one has drained and fills the straggler "
+                                      "tail of the other group's launch.  Every step's work completes inside the timed region" % G) if G > 1 else "none",
+                       "replayed_rounds": R, "l2": "per-step working set (0.45 MB per instance x batch_per_gpu) larger than the 126 MB L2 at N <= 2; "
+                                                   "in addition a 256 MiB buffer is written between the steps of one group",
                        "sharding": "contiguous instance blocks per rank, no data-path collective; one NCCL all-gather of 16 B/instance at the end"},
             "qp_solves_per_sec": units_all / (t_max * 1e-3),
+            "timed_regions_ms": {"device": [round(t, 3) for t, _ in dev_regions], "host": [round(t, 3) for t, _ in host_regions],
+                                 "note": "each region = exactly `steps` steps after the warm-up, bracketed by a barrier + synchronize; the "
+                                         "MEDIAN region is reported (rank 0's regions shown)"},
             "e2e": {"value": e_units_all / (e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e_max / args.steps,
                     "note": "host buffers in, host buffers out through sqpqp_update_nlp / merit / kt_residuals / solve_tr; the caller's persistent "
@@ -589,7 +685,10 @@ def main():
                                             if traffic else None),
                          "kernel": kernel_name,  # from the library (sqpqp_last_solve_kernel): the launch rule lives there
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "note": "achieved = algorithmic bytes / CUDA-event duration of the solve kernel; bytes = per-instance fp64 values each "
+                         "achieved_one_launch_at_a_time": ach_alone,
+                         "note": "achieved = algorithmic bytes of every solve launch of the timed region / device time of the region (launches of the "
+                                 "groups overlap; achieved_one_launch_at_a_time: the same launches run alone, bytes / sum of their CUDA-event "
+                                 "durations); bytes = per-instance fp64 values each "
                                  "phase of an interior-point iteration must touch once (%d B per iteration + %d B per Cholesky factorisation, "
                                  "DESIGN.md 5) x the device-counted iterations/factorisations of every instance in the launch + the shared int32 "
                                  "index programs once.  The kernel is bound by dependent-load latency of the level-scheduled sparse "
@@ -611,15 +710,16 @@ def main():
         if not args.no_device_eval and world == 1:
             # the same full batched SQP solve with f, grad f, g, J and H values evaluated on the device (csrc/acopf.cuh,
             # SURVEY 8f rank 1) instead of by the host callbacks: only x and lambda go up per round
-            sqp2 = BatchSqpTR(nlp, Bl, Parameters(**kw), device=local, device_evaluator=True)
-            sqp2.mixed_phases = not args.sequential_phases
+            sqp2 = GroupedBatchSqpTR(nlp, Bl, Parameters(**kw), groups=G, device=local, device_evaluator=True)
+            for sub in sqp2.subs:
+                sub.mixed_phases = not args.sequential_phases
             t0 = time.perf_counter()
             sqp2.run()
             line["full_sqp_solve_device_evaluator"] = {
-                "wall_s": time.perf_counter() - t0, "rounds": int(sqp2.rounds), "qp_solves": int(sqp2.n_qp.sum()),
+                "wall_s": time.perf_counter() - t0, "groups": G, "rounds": int(sqp2.rounds), "qp_solves": int(sqp2.n_qp.sum()),
                 "status_counts": {int(k): int(v) for k, v in zip(*np.unique(sqp2.status, return_counts=True))},
                 "device_s": sqp2.timers["device"], "callbacks_s": sqp2.timers["callbacks"],
-                "solve_kernel_s": sqp2.optimizer.stats["solve_ms"] / 1e3,
+                "solve_kernel_s": sqp2.stats["solve_ms"] / 1e3,
                 "max_rel_objective_diff_vs_host_evaluator": float(np.max(np.abs(sqp2.obj_val - sqp.obj_val) / np.maximum(1.0, np.abs(sqp.obj_val))))}
             sqp2.close()
         if not args.no_cpu_baseline and world == 1:
@@ -627,11 +727,12 @@ def main():
             import multiprocessing as mp
             jobs = []
             k = 0
+            B0 = gb[0][1] - gb[0][0]  # subproblems of group 0 (instances gb[0][0] .. of the shard)
             while len(jobs) < max(6, args.cpu_sample + 1) and k < 64 * R:
-                r = rec[k % R]
-                b = (k // R) % Bl
+                r = rec[0][k % R]
+                b = (k // R) % B0
                 if r["qp"][b]:
-                    jobs.append((net, pd[b], qd[b], {"dE": r["dE"][b], "h_val": r["h_val"][b], "df": r["df"][b],
+                    jobs.append((net, pd[gb[0][0] + b], qd[gb[0][0] + b], {"dE": r["dE"][b], "h_val": r["h_val"][b], "df": r["df"][b],
                                                      "E": r["E"][b], "x": r["x"][b], "Delta": float(r["Delta"][b])}))
                 k += 1
             tcb0 = time.perf_counter()

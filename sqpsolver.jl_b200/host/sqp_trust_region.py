@@ -370,6 +370,74 @@ class BatchSqpTR:
         self.optimizer.close()
 
 
+class GroupedBatchSqpTR:
+    """A batch driven as G independent GROUPS of instances, one :class:`BatchSqpTR` (its own engine handle and stream) and one
+    host thread per group.
+
+    The instances of a batch never interact, so nothing forces them through the SQP rounds in lock step.  With
+    one group the GPU idles at the end of every solve launch while the few slow subproblems finish (15-24 % of a 1024-instance
+    launch, profiles/r02_tuning.md section 8), and it idles completely while the host evaluates the NLP callbacks and the
+    ratio test.  With G >= 2 groups the launches of the other groups fill both gaps: a group's next round is queued as soon
+    as ITS slowest instance and ITS host work are done.  Same per-instance arithmetic and results as :class:`BatchSqpTR`
+    (every group is one); only the order in which the hardware sees the work changes.
+
+    ``nlp.subset(lo, hi)`` must return the NLP of instances lo..hi-1 (per-instance data sliced)."""
+
+    def __init__(self, nlp, batch: int, params: Parameters | None = None, groups: int = 2, device: int = 0,
+                 engine_options: dict | None = None, x0=None, device_evaluator: bool = False, layout: dict | None = None):
+        self.problem, self.B = nlp, batch
+        G = max(1, min(int(groups), batch))
+        self.bounds = [(g * batch // G, (g + 1) * batch // G) for g in range(G)]
+        self.subs = []
+        if G > 1:  # the hand-off to the resident launch assumes that a shard has the GPU to itself (one wave): off for groups
+            layout = dict(layout or {})
+            layout.setdefault("handoff", 0)
+        for lo, hi in self.bounds:
+            x0g = None if x0 is None or np.ndim(x0) == 1 else np.asarray(x0)[lo:hi]
+            self.subs.append(BatchSqpTR(nlp.subset(lo, hi), hi - lo, params, device=device, engine_options=engine_options,
+                                        x0=x0 if x0g is None else x0g, device_evaluator=device_evaluator, layout=layout))
+        self.options = self.subs[0].options
+
+    def run(self, log=None):
+        import threading
+        errs = []
+
+        logs = [([] if log is not None else None) for _ in self.subs]
+
+        def work(sub, lg):
+            try:
+                sub.run(lg)
+            except BaseException as e:  # noqa: BLE001 -- re-raised in the caller's thread
+                errs.append(e)
+
+        t0 = time.perf_counter()
+        threads = [threading.Thread(target=work, args=(s, lg)) for s, lg in zip(self.subs, logs)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
+        self.elapsed = time.perf_counter() - t0
+        if log is not None:  # instance ids of the whole batch
+            for (lo, _), lg in zip(self.bounds, logs):
+                for e in lg:
+                    e["b"] += lo
+                    log.append(e)
+        cat = lambda name: np.concatenate([getattr(s, name) for s in self.subs])  # noqa: E731
+        for name in ("x", "lam", "mult_x_L", "mult_x_U", "mult_g", "obj_val", "status", "ret", "n_qp", "iter", "prim_infeas",
+                     "dual_infeas", "f"):
+            setattr(self, name, cat(name))
+        self.rounds = max(s.rounds for s in self.subs)
+        self.timers = {k: sum(s.timers[k] for s in self.subs) for k in self.subs[0].timers}
+        self.stats = {k: sum(s.optimizer.stats[k] for s in self.subs) for k in self.subs[0].optimizer.stats}
+        return self
+
+    def close(self):
+        for s in self.subs:
+            s.close()
+
+
 class SqpTR:
     """Single-instance view of :class:`BatchSqpTR` (the reference's ``SqpTR``)."""
 

@@ -35,6 +35,12 @@ INF = np.inf
 
 
 class AcopfPolar(NLP):
+    def subset(self, lo: int, hi: int) -> "AcopfPolar":
+        """The NLP of instances lo..hi-1 of a batched (per-instance loads) problem; an unbatched problem is its own subset."""
+        if self.pd.ndim == 1:
+            return self
+        return AcopfPolar(self.net, pd=self.pd[lo:hi], qd=self.qd[lo:hi])
+
     def __init__(self, net: Network, pd=None, qd=None):
         self.net = net
         self.name = f"acopf_{net.name}"

@@ -318,6 +318,28 @@ def test_batched_instances_match_individual_oracle_runs(built_lib):
     bt.close()
 
 
+@pytest.mark.parametrize("device_evaluator", [False, True])
+def test_grouped_driver_gives_the_lock_step_results(built_lib, device_evaluator):
+    """GroupedBatchSqpTR: the batch as independent groups of instances, one engine handle / stream / host thread per group, so
+    that the launches and the host work of the groups overlap.  Instances never interact, so every instance must end where the
+    lock-step BatchSqpTR takes it: same status, iteration count, number of subproblems, x and objective (the same kernels run
+    every instance on the same data)."""
+    from sqpsolver_jl_b200.host.sqp_trust_region import GroupedBatchSqpTR
+    net = case9()
+    B = 7  # groups of unequal size
+    pd, qd = net.perturbed_loads(B, rel_sigma=0.05, seed=1234)
+    kw = dict(max_iter=60, init_mu=1e4)
+    one = BatchSqpTR(AcopfPolar(net, pd=pd, qd=qd), B, Parameters(**kw), device_evaluator=device_evaluator).run()
+    log = []
+    grp = GroupedBatchSqpTR(AcopfPolar(net, pd=pd, qd=qd), B, Parameters(**kw), groups=3, device_evaluator=device_evaluator).run(log)
+    assert [hi - lo for lo, hi in grp.bounds] == [2, 2, 3]
+    assert np.array_equal(grp.status, one.status) and (one.status == 0).sum() >= B - 1
+    assert np.array_equal(grp.iter, one.iter) and np.array_equal(grp.n_qp, one.n_qp)
+    assert np.abs(grp.x - one.x).max() <= 1e-12 and np.abs(grp.obj_val - one.obj_val).max() <= 1e-9 * np.abs(one.obj_val).max()
+    assert sorted({e["b"] for e in log}) == list(range(B))  # the log carries batch-wide instance ids
+    one.close(); grp.close()
+
+
 @pytest.mark.parametrize("indefinite", [False, True])
 def test_full_size_batch_kkt_property(built_lib, indefinite):
     """BASELINE configs[4] at full size (1024 perturbed-load case118-shaped instances, one shared pattern): every
