@@ -394,6 +394,9 @@ def main():
     # (cont.) finer groups keep helping until a group has about 32 instances: 256 per GPU 28.7 / 22.3 / 22.0 / 19.2 ms with
     # 1 / 2 / 4 / 8 groups, 128 per GPU 18.7 / 18.4 / 17.5 / 17.8 / 26.9 with 1 / 2 / 4 / 8 / 16, 512 per GPU 35.9 / 33.7 with 2 / 4
     G = args.groups if args.groups > 0 else (4 if Bl >= 512 else max(2, min(8, Bl // 32)))
+    # every group has a host thread (the host-buffer C ABI blocks): keep them within the cores of the node
+    if args.groups <= 0:
+        G = min(G, max(2, (os.cpu_count() or 16) // max(1, world)))
     G = max(1, min(G, Bl))
     layout = dict(G=args.layout_G, threads=args.layout_threads, ctas_per_sm=args.layout_ctas, tail=args.layout_tail)
     if args.layout_handoff is not None:
