@@ -668,8 +668,10 @@ def main():
                                       "(host/sqp_trust_region.py: GroupedBatchSqpTR); the K timed steps of every group are enqueued back to "
                                       "back, so a group's next launch starts when ITS previous one has drained and fills the straggler "
                                       "tail of the other group's launch.  Every step's work completes inside the timed region" % G) if G > 1 else "none",
-                       "replayed_rounds": R, "l2": "per-step working set (0.45 MB per instance x batch_per_gpu) larger than the 126 MB L2 at N <= 2; "
-                                                   "in addition a 256 MiB buffer is written between the steps of one group",
+                       "replayed_rounds": R, "l2": "inputs larger than L2: consecutive steps replay DIFFERENT recorded rounds (%d input sets of %.0f MB "
+                                                   "per GPU, cycled), and the per-instance work arrays (0.45 MB x batch_per_gpu) are rewritten by "
+                                                   "every solve; in addition a 256 MiB buffer is written between the steps of one group"
+                                                   % (R, h2d / 1e6),
                        "sharding": "contiguous instance blocks per rank, no data-path collective; one NCCL all-gather of 16 B/instance at the end"},
             "qp_solves_per_sec": units_all / (t_max * 1e-3),
             "timed_regions_ms": {"device": [round(t, 3) for t, _ in dev_regions], "host": [round(t, 3) for t, _ in host_regions],
@@ -677,7 +679,9 @@ def main():
                                          "MEDIAN region is reported (rank 0's regions shown)"},
             "e2e": {"value": e_units_all / (e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e_max / args.steps,
-                    "note": "host buffers in, host buffers out through sqpqp_update_nlp / merit / kt_residuals / solve_tr; the caller's persistent "
+                    "host_threads": G,
+                    "note": "host buffers in, host buffers out through sqpqp_update_nlp / merit / kt_residuals / solve_tr(_mixed), one host thread "
+                            "per group (the calls block); the caller's persistent "
                             "arrays (inputs and results) are page-locked once with sqpqp_host_register, so every step copies them "
                             "straight over the link (H2D and D2H inside the timed region, no staging memcpy)"},
             "gpu_launches": int(launches_all),

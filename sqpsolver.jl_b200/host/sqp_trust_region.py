@@ -394,7 +394,8 @@ class GroupedBatchSqpTR:
             layout.setdefault("handoff", 0)
         for lo, hi in self.bounds:
             x0g = None if x0 is None or np.ndim(x0) == 1 else np.asarray(x0)[lo:hi]
-            self.subs.append(BatchSqpTR(nlp.subset(lo, hi), hi - lo, params, device=device, engine_options=engine_options,
+            sub_nlp = nlp.subset(lo, hi) if hasattr(nlp, "subset") else nlp  # an NLP without per-instance data is its own subset
+            self.subs.append(BatchSqpTR(sub_nlp, hi - lo, params, device=device, engine_options=engine_options,
                                         x0=x0 if x0g is None else x0g, device_evaluator=device_evaluator, layout=layout))
         self.options = self.subs[0].options
 
